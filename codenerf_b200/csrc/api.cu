@@ -1,0 +1,192 @@
+// api.cu -- the extern "C" boundary declared in include/codenerf_b200.h: argument
+// validation and dispatch to the tcgen05 (bf16) or CUDA-core (fp32) implementation.
+#include "common.cuh"
+#include "mlp_fp32.cuh"
+#include "render_sm100.cuh"
+
+std::atomic<long long> g_cnb_launches{0};
+
+extern "C" int cnb_version(void) { return 100; }
+
+extern "C" int64_t cnb_launch_count(void) { return (int64_t)g_cnb_launches.load(); }
+
+extern "C" const char* cnb_strerror(int status) {
+    switch (status) {
+        case CNB_OK: return "ok";
+        case CNB_E_INVALID: return "codenerf_b200: invalid argument";
+        case CNB_E_UNSUPPORTED: return "codenerf_b200: unsupported network shape or sample count";
+        case CNB_E_WORKSPACE: return "codenerf_b200: workspace missing or too small";
+        case CNB_E_ALIGNMENT: return "codenerf_b200: pointer alignment";
+        case CNB_E_DEVICE: return "codenerf_b200: device is not sm_100 (B200)";
+        default: break;
+    }
+    if (status > 0) return cudaGetErrorString((cudaError_t)status);
+    return "codenerf_b200: unknown status";
+}
+
+extern "C" int cnb_check_device(void) {
+    int dev = 0;
+    CNB_CUDA_TRY(cudaGetDevice(&dev));
+    int major = 0;
+    CNB_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    return major == 10 ? CNB_OK : CNB_E_DEVICE;
+}
+
+extern "C" int64_t cnb_param_count(const cnb_net_config* cfg) {
+    if (cnb_validate_config(cfg) != CNB_OK) return -1;
+    CnbLayout L; cnb_make_layout(cfg, &L);
+    return L.total;
+}
+
+extern "C" int cnb_num_param_tensors(const cnb_net_config* cfg) {
+    if (cnb_validate_config(cfg) != CNB_OK) return -1;
+    CnbLayout L; cnb_make_layout(cfg, &L);
+    return L.n_tensors;
+}
+
+extern "C" int cnb_param_layout(const cnb_net_config* cfg, int64_t* offsets, int32_t* rows, int32_t* cols) {
+    CNB_TRY(cnb_validate_config(cfg));
+    if (!offsets || !rows || !cols) return CNB_E_INVALID;
+    CnbLayout L; cnb_make_layout(cfg, &L);
+    const int W = cfg->W, LD = cfg->latent_dim;
+    int t = 0;
+    auto put = [&](int64_t woff, int64_t boff, int r, int c) {
+        offsets[t] = woff; rows[t] = r; cols[t] = c; ++t;
+        offsets[t] = boff; rows[t] = r; cols[t] = 1; ++t;
+    };
+    put(L.enc_xyz_w, L.enc_xyz_b, W, L.d_xyz);
+    for (int j = 0; j < cfg->shape_blocks; ++j) { put(L.sl_w[j], L.sl_b[j], W, LD); put(L.s_w[j], L.s_b[j], W, W); }
+    put(L.enc_shape_w, L.enc_shape_b, W, W);
+    put(L.sigma_w, L.sigma_b, 1, W);
+    put(L.enc_vd_w, L.enc_vd_b, W, W + L.d_dir);
+    for (int j = 0; j < cfg->texture_blocks; ++j) { put(L.tl_w[j], L.tl_b[j], W, LD); put(L.t_w[j], L.t_b[j], W, W); }
+    put(L.rgb0_w, L.rgb0_b, W / 2, W);
+    put(L.rgb2_w, L.rgb2_b, 3, W / 2);
+    return t == L.n_tensors ? CNB_OK : CNB_E_INVALID;
+}
+
+static int check_params(const cnb_net_config* cfg, const float* const* params) {
+    CNB_TRY(cnb_validate_config(cfg));
+    if (!params) return CNB_E_INVALID;
+    CnbLayout L; cnb_make_layout(cfg, &L);
+    for (int i = 0; i < L.n_tensors; ++i) if (!params[i]) return CNB_E_INVALID;
+    return CNB_OK;
+}
+
+// ---------------------------------------------------------------------------
+extern "C" size_t cnb_packed_weights_bytes(const cnb_net_config* cfg) {
+    if (cnb_validate_config(cfg) != CNB_OK) return 0;
+    return cnb_sm100_packed_bytes(cfg);
+}
+
+extern "C" int cnb_pack_weights(const cnb_net_config* cfg, const float* const* params, void* packed,
+                                cnb_stream_t stream) {
+    CNB_TRY(check_params(cfg, params));
+    if (!packed) return CNB_E_INVALID;
+    return cnb_sm100_pack_weights(cfg, params, packed, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+extern "C" size_t cnb_mlp_workspace_bytes(const cnb_net_config* cfg, int64_t S, int n_codes, int precision,
+                                          int backward) {
+    if (cnb_validate_config(cfg) != CNB_OK || S <= 0 || n_codes < 1) return 0;
+    if (precision == CNB_PRECISION_FP32) return cnb_fp32_workspace_bytes(cfg, S, 0, n_codes, backward, 0);
+    return cnb_sm100_mlp_workspace_bytes(cfg, S, n_codes, backward);
+}
+
+extern "C" int cnb_mlp_forward(const cnb_net_config* cfg, const float* const* params, const void* packed,
+                               const float* xyz, const float* viewdir, const float* shape_codes,
+                               const float* texture_codes, int n_codes, int64_t samples_per_code, int64_t S,
+                               int precision, float* sigmas, float* rgbs, void* workspace, size_t workspace_bytes,
+                               cnb_stream_t stream) {
+    CNB_TRY(check_params(cfg, params));
+    if (S < 0 || !xyz || !viewdir || !shape_codes || !texture_codes || n_codes < 1 || !sigmas || !rgbs)
+        return CNB_E_INVALID;
+    if (n_codes > 1 && samples_per_code < 1) return CNB_E_INVALID;
+    if (S == 0) return CNB_OK;
+    if (precision == CNB_PRECISION_FP32)
+        return cnb_fp32_mlp_forward(cfg, params, xyz, viewdir, shape_codes, texture_codes, n_codes,
+                                    n_codes > 1 ? samples_per_code : 0, S, sigmas, rgbs, workspace, workspace_bytes,
+                                    (cudaStream_t)stream);
+    if (precision != CNB_PRECISION_BF16) return CNB_E_INVALID;
+    if (!packed) return CNB_E_INVALID;
+    return cnb_sm100_mlp_forward(cfg, params, packed, xyz, viewdir, shape_codes, texture_codes, n_codes,
+                                 n_codes > 1 ? samples_per_code : 0, S, sigmas, rgbs, workspace, workspace_bytes,
+                                 (cudaStream_t)stream);
+}
+
+extern "C" int cnb_mlp_backward(const cnb_net_config* cfg, const float* const* params, const void* packed,
+                                const float* xyz, const float* viewdir, const float* shape_codes,
+                                const float* texture_codes, int n_codes, int64_t samples_per_code, int64_t S,
+                                int precision, const float* d_sigmas, const float* d_rgbs, float* d_params,
+                                float* d_shape_codes, float* d_texture_codes, void* workspace, size_t workspace_bytes,
+                                cnb_stream_t stream) {
+    CNB_TRY(check_params(cfg, params));
+    if (S <= 0 || !xyz || !viewdir || !shape_codes || !texture_codes || n_codes < 1 || !d_sigmas || !d_rgbs ||
+        !d_shape_codes || !d_texture_codes)
+        return CNB_E_INVALID;
+    if (n_codes > 1 && samples_per_code < 1) return CNB_E_INVALID;
+    if (precision == CNB_PRECISION_FP32)
+        return cnb_fp32_mlp_backward(cfg, params, xyz, viewdir, shape_codes, texture_codes, n_codes,
+                                     n_codes > 1 ? samples_per_code : 0, S, d_sigmas, d_rgbs, d_params, d_shape_codes,
+                                     d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
+    if (precision != CNB_PRECISION_BF16) return CNB_E_INVALID;
+    if (!packed) return CNB_E_INVALID;
+    return cnb_sm100_mlp_backward(cfg, params, packed, xyz, viewdir, shape_codes, texture_codes, n_codes,
+                                  n_codes > 1 ? samples_per_code : 0, S, d_sigmas, d_rgbs, d_params, d_shape_codes,
+                                  d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------
+extern "C" size_t cnb_render_workspace_bytes(const cnb_net_config* cfg, const cnb_ray_batch* rays, int precision,
+                                             int backward) {
+    if (cnb_validate_config(cfg) != CNB_OK || cnb_validate_rays(rays) != CNB_OK) return 0;
+    if (precision == CNB_PRECISION_FP32)
+        return cnb_fp32_workspace_bytes(cfg, rays->n_rays * rays->n_samples, rays->n_samples, rays->n_codes, backward, 1);
+    return cnb_sm100_render_workspace_bytes(cfg, rays, backward);
+}
+
+static int render_dispatch(const cnb_net_config* cfg, const float* const* params, const void* packed,
+                           const cnb_ray_batch* rays, int precision, int mode, const float* d_rgb,
+                           const float* d_depth, const float* target, float loss_scale, float* rgb, float* depth,
+                           float* acc, float* sq_err, float* d_params, float* d_shape, float* d_tex, void* ws,
+                           size_t ws_bytes, cnb_stream_t stream) {
+    CNB_TRY(check_params(cfg, params));
+    CNB_TRY(cnb_validate_rays(rays));
+    if (mode == 0 && (!rgb || !depth)) return CNB_E_INVALID;
+    if (mode == 1 && (!d_rgb || !d_shape || !d_tex)) return CNB_E_INVALID;
+    if (mode == 2 && (!target || !d_shape || !d_tex)) return CNB_E_INVALID;
+    if (precision == CNB_PRECISION_FP32)
+        return cnb_fp32_render(cfg, params, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc, sq_err,
+                               d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
+    if (precision != CNB_PRECISION_BF16) return CNB_E_INVALID;
+    if (!packed) return CNB_E_INVALID;
+    return cnb_sm100_render(cfg, params, packed, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc,
+                            sq_err, d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int cnb_render_forward(const cnb_net_config* cfg, const float* const* params, const void* packed,
+                                  const cnb_ray_batch* rays, int precision, float* rgb, float* depth, float* acc,
+                                  void* workspace, size_t workspace_bytes, cnb_stream_t stream) {
+    return render_dispatch(cfg, params, packed, rays, precision, 0, nullptr, nullptr, nullptr, 1.f, rgb, depth, acc,
+                           nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+extern "C" int cnb_render_backward(const cnb_net_config* cfg, const float* const* params, const void* packed,
+                                   const cnb_ray_batch* rays, int precision, const float* d_rgb, const float* d_depth,
+                                   float* d_params, float* d_shape_codes, float* d_texture_codes, void* workspace,
+                                   size_t workspace_bytes, cnb_stream_t stream) {
+    return render_dispatch(cfg, params, packed, rays, precision, 1, d_rgb, d_depth, nullptr, 1.f, nullptr, nullptr,
+                           nullptr, nullptr, d_params, d_shape_codes, d_texture_codes, workspace, workspace_bytes,
+                           stream);
+}
+
+extern "C" int cnb_render_train_step(const cnb_net_config* cfg, const float* const* params, const void* packed,
+                                     const cnb_ray_batch* rays, int precision, const float* target, float loss_scale,
+                                     float* rgb, float* depth, float* acc, float* sq_err_sum, float* d_params,
+                                     float* d_shape_codes, float* d_texture_codes, void* workspace,
+                                     size_t workspace_bytes, cnb_stream_t stream) {
+    return render_dispatch(cfg, params, packed, rays, precision, 2, nullptr, nullptr, target, loss_scale, rgb, depth,
+                           acc, sq_err_sum, d_params, d_shape_codes, d_texture_codes, workspace, workspace_bytes,
+                           stream);
+}
