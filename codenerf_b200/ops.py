@@ -102,6 +102,8 @@ def volume_rendering_forward(sigmas, rgbs, z_vals, white_bg):
     rgb = torch.empty(B, 3, dtype=torch.float32, device=sigmas.device)
     depth = torch.empty(B, dtype=torch.float32, device=sigmas.device)
     acc = torch.empty(B, dtype=torch.float32, device=sigmas.device)
+    if B == 0:
+        return rgb, depth, acc
     with torch.cuda.device(sigmas.device):
         _lib.check(L.cnb_volume_rendering_forward(_ptr(sigmas), _ptr(rgbs), _ptr(z_vals), B, N, int(bool(white_bg)),
                                                   _ptr(rgb), _ptr(depth), _ptr(acc), _stream()))
@@ -114,6 +116,8 @@ def volume_rendering_backward(sigmas, rgbs, z_vals, white_bg, d_rgb, d_depth):
     B = sigmas.numel() // N
     ds = torch.empty(B, N, dtype=torch.float32, device=sigmas.device)
     dc = torch.empty(B, N, 3, dtype=torch.float32, device=sigmas.device)
+    if B == 0:
+        return ds, dc
     with torch.cuda.device(sigmas.device):
         _lib.check(L.cnb_volume_rendering_backward(_ptr(sigmas), _ptr(rgbs), _ptr(z_vals), B, N, int(bool(white_bg)),
                                                    _ptr(d_rgb), _ptr(d_depth), _ptr(ds), _ptr(dc), _stream()))
