@@ -49,7 +49,7 @@ EXPORTS = [
     "cnb_param_layout", "cnb_get_rays", "cnb_sample_from_rays", "cnb_volume_rendering_forward",
     "cnb_volume_rendering_backward", "cnb_packed_weights_bytes", "cnb_pack_weights", "cnb_mlp_workspace_bytes",
     "cnb_mlp_forward", "cnb_mlp_backward", "cnb_render_workspace_bytes", "cnb_render_forward",
-    "cnb_render_backward", "cnb_render_train_step", "cnb_launch_count",
+    "cnb_render_backward", "cnb_render_train_step", "cnb_launch_count", "cnb_debug_pipeline_timeouts",
 ]
 
 _lib = None
@@ -108,6 +108,7 @@ def load():
     L.cnb_render_train_step.argtypes = [cfgp, ctypes.POINTER(vp), vp, rayp, i32, vp, f32, vp, vp, vp, vp, vp, vp, vp,
                                         vp, sz, vp]
     L.cnb_launch_count.restype = i64
+    L.cnb_debug_pipeline_timeouts.restype = i32
     _lib = L
     return L
 

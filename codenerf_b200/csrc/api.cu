@@ -24,6 +24,8 @@ extern "C" const char* cnb_strerror(int status) {
     return "codenerf_b200: unknown status";
 }
 
+extern "C" int cnb_debug_pipeline_timeouts(void) { return cnb_sm100_pipeline_timeouts(); }
+
 extern "C" int cnb_check_device(void) {
     int dev = 0;
     CNB_CUDA_TRY(cudaGetDevice(&dev));

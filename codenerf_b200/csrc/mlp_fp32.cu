@@ -287,6 +287,23 @@ __global__ void k_l2_seed(const float* __restrict__ rgb, const float* __restrict
     if (sq_err) atomicAdd(sq_err + (ray0 + r) / rays_per_segment, e2);
 }
 
+// Launch wrappers shared with the tensor-core path (render_sm100.cu).
+int cnb_launch_latent_fwd(const float* Wl, const float* bl, const float* codes, int n_codes, int LD, int W,
+                          float* z, int64_t ldz, cudaStream_t st) {
+    const int threads = 256;
+    const int blocks = (n_codes * W * 32 + threads - 1) / threads;
+    k_latent_fwd<<<blocks, threads, 0, st>>>(Wl, bl, codes, n_codes, LD, W, z, ldz);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+}
+int cnb_launch_latent_bwd(const float* Wl, const float* codes, const float* z, const float* dz, int64_t ldz,
+                          int n_codes, int LD, int W, float* dW, float* db, float* dcodes, cudaStream_t st) {
+    dim3 grid(W, n_codes);
+    k_latent_bwd<<<grid, 128, 0, st>>>(Wl, codes, z, dz, ldz, n_codes, LD, W, dW, db, dcodes);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+}
+
 // ===========================================================================
 // Host orchestration
 

@@ -16,3 +16,10 @@ int cnb_fp32_render(const cnb_net_config* cfg, const float* const* params, const
                     const float* d_rgb, const float* d_depth, const float* target, float loss_scale,
                     float* rgb, float* depth, float* acc, float* sq_err,
                     float* d_params, float* d_shape, float* d_tex, void* ws, size_t ws_bytes, cudaStream_t st);
+
+// z[code][n] = ReLU(Wl[n,:] . codes[code,:] + bl[n])  -- reference src/model.py:41, :49
+int cnb_launch_latent_fwd(const float* Wl, const float* bl, const float* codes, int n_codes, int LD, int W,
+                          float* z, int64_t ldz, cudaStream_t st);
+// dpre = dz * (z > 0); dW += dpre (x) code; db += dpre; dcodes += Wl^T dpre   (dW / db may be null)
+int cnb_launch_latent_bwd(const float* Wl, const float* codes, const float* z, const float* dz, int64_t ldz,
+                          int n_codes, int LD, int W, float* dW, float* db, float* dcodes, cudaStream_t st);

@@ -1,9 +1,683 @@
-// TEMPORARY stub (replaced by the tcgen05 implementation).
+// render_sm100.cu -- CNB_PRECISION_BF16: the fused CodeNeRF render path on Blackwell tensor
+// cores.  Hand-written sm_100a: tcgen05.mma (bf16 x bf16 -> fp32 in TMEM), weights streamed
+// through shared memory by the TMA engine (1-D bulk copies of pre-swizzled stage images),
+// mbarrier pipelines, warp-specialised roles.
+//
+// K1  k_render_fwd : [ray gen + sampling +] positional encoding -> 8 chained GEMM layers whose
+//      activations live only in shared memory / TMEM -> sigma & rgb heads in the epilogue ->
+//      per-ray transmittance scan + alpha compositing.  sigmas / rgbs never reach HBM
+//      (unless the caller asks for them: unfused CodeNeRF.forward, or the training spill).
+//
+// Reference semantics: src/model.py:36-53 (network), src/utils.py:10-47 (rays, sampling,
+// compositing).  See DESIGN.md for the tile / pipeline design and the roofline arithmetic.
 #include "render_sm100.cuh"
-size_t cnb_sm100_packed_bytes(const cnb_net_config*) { return 256; }
-int cnb_sm100_pack_weights(const cnb_net_config*, const float* const*, void*, cudaStream_t) { return CNB_OK; }
-size_t cnb_sm100_mlp_workspace_bytes(const cnb_net_config*, int64_t, int, int) { return 256; }
-size_t cnb_sm100_render_workspace_bytes(const cnb_net_config*, const cnb_ray_batch*, int) { return 256; }
-int cnb_sm100_mlp_forward(const cnb_net_config*, const float* const*, const void*, const float*, const float*, const float*, const float*, int, int64_t, int64_t, float*, float*, void*, size_t, cudaStream_t) { return CNB_E_UNSUPPORTED; }
-int cnb_sm100_mlp_backward(const cnb_net_config*, const float* const*, const void*, const float*, const float*, const float*, const float*, int, int64_t, int64_t, const float*, const float*, float*, float*, float*, void*, size_t, cudaStream_t) { return CNB_E_UNSUPPORTED; }
-int cnb_sm100_render(const cnb_net_config*, const float* const*, const void*, const cnb_ray_batch*, int, const float*, const float*, const float*, float, float*, float*, float*, float*, float*, float*, float*, void*, size_t, cudaStream_t) { return CNB_E_UNSUPPORTED; }
+#include "mlp_fp32.cuh"
+#include "umma.cuh"
+
+namespace {
+
+constexpr int kW = 256;                 // layer width the tensor-core path implements
+constexpr int kLx = 10, kLd = 4;        // PE frequencies (63 / 27 channels)
+constexpr int kTileRows = 128;          // UMMA M
+constexpr int kSlot = 16384;            // one weight stage: [128 n x 64 k] bf16, 128-B swizzle
+constexpr int kNumStages = 4;
+constexpr int kABlock = 16384;          // activation K-block [128 rows x 64] bf16, 128-B swizzle
+constexpr int kDirBlock = 8192;         // PE(viewdir) block [128 rows x 32] bf16, 64-B swizzle
+constexpr int kATile = 4 * kABlock + kDirBlock;
+constexpr int kThreads = 320;           // warp 0 producer, warp 1 MMA, warps 2-5 group X, 6-9 group Y
+constexpr int kMaxLayers = 2 * CNB_MAX_BLOCKS + 4;
+
+struct FwdLayer {
+    uint32_t w_off;       // byte offset of the first stage slot inside the packed buffer
+    uint8_t n_kchunks;    // 64-wide K chunks taken from activation blocks 0..n-1
+    uint8_t has_dir;      // one more K=32 chunk from the PE(viewdir) block
+    uint8_t n_halves;     // n_out / 128
+    uint8_t relu;
+    uint8_t kind;         // 0 hidden, 1 encoding_shape (+ sigma head), 2 rgb.0 (+ rgb head)
+    int8_t folded;        // >= 0: bias row of the per-code folded table; < 0: shared bias
+    uint16_t pad;
+    const float* bias;    // shared bias [n_out] (fp32 parameter tensor)
+};
+
+struct FwdParams {
+    int n_layers;
+    FwdLayer layers[kMaxLayers];
+    const uint8_t* packed;
+    const float* folded;          // [n_codes][n_folded][256]: b_j + W_j z_j  (z_j = ReLU(latent layer))
+    int n_folded, n_codes;
+    int64_t rows_per_code;
+    const float *w_sigma, *b_sigma, *w_rgb2, *b_rgb2;
+    int mode;                     // 0: rays -> composite; 1: xyz / viewdir arrays -> sigmas, rgbs
+    CnbRaySource rs;
+    const float *xyz, *viewdir;
+    int64_t n_rays, S;
+    int white_bg, ring_cap;
+    float *rgb, *depth, *acc;
+    float4* samples_out;          // optional per-sample (sigma, r, g, b) spill for the training backward
+    float *sigmas, *rgbs;
+};
+
+__device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(umma::smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+
+// PE of one row into the operand blocks -- reference src/model.py:4-7 (x, sines, cosines).
+// sin/cos(2^i x) by exact doubling from an accurate sincosf(x): error < 2^i * 1e-7, far below bf16.
+__device__ __forceinline__ void encode_row(const float p[3], const float v[3], bool valid, uint8_t* blk0,
+                                           uint8_t* dirblk, int row) {
+    float e[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) e[i] = 0.f;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            e[k] = p[k];
+            float s, c;
+            sincosf(p[k], &s, &c);
+#pragma unroll
+            for (int i = 0; i < kLx; ++i) {
+                e[3 + 3 * i + k] = s;
+                e[3 + 3 * kLx + 3 * i + k] = c;
+                const float s2 = 2.f * s * c;
+                c = fmaf(-2.f * s, s, 1.f);
+                s = s2;
+            }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        st_shared_v4(blk0 + row * 128 + ((ch ^ (row & 7)) << 4), umma::pack_bf16(e[ch * 8 + 0], e[ch * 8 + 1]),
+                     umma::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]), umma::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]),
+                     umma::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
+    }
+    float d[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) d[i] = 0.f;
+    if (valid) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            d[k] = v[k];
+            float s, c;
+            sincosf(v[k], &s, &c);
+#pragma unroll
+            for (int i = 0; i < kLd; ++i) {
+                d[3 + 3 * i + k] = s;
+                d[3 + 3 * kLd + 3 * i + k] = c;
+                const float s2 = 2.f * s * c;
+                c = fmaf(-2.f * s, s, 1.f);
+                s = s2;
+            }
+        }
+    }
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+        st_shared_v4(dirblk + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4), umma::pack_bf16(d[ch * 8 + 0], d[ch * 8 + 1]),
+                     umma::pack_bf16(d[ch * 8 + 2], d[ch * 8 + 3]), umma::pack_bf16(d[ch * 8 + 4], d[ch * 8 + 5]),
+                     umma::pack_bf16(d[ch * 8 + 6], d[ch * 8 + 7]));
+    }
+}
+
+__device__ __forceinline__ float warp_excl_prod_f(float local, int lane) {
+    float incl = local;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl *= up;
+    }
+    const float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    return lane == 0 ? 1.f : excl;
+}
+
+// Alpha compositing of one ray by one warp from the shared-memory sample ring --
+// reference src/utils.py:34-47 (exclusive transmittance product, white background).
+__device__ __forceinline__ void composite_ray(const FwdParams& p, const float4* ring, int ring_cap, int64_t lrow0,
+                                              int64_t gray, int lane) {
+    const int N = p.rs.N;
+    const int64_t seg = gray / p.rs.rays_per_segment;
+    const float* z = p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0);
+    const int per = (N + 31) >> 5;
+    const int i0 = lane * per;
+    float T_local = 1.f;
+    for (int j = 0; j < per; ++j) {
+        const int i = i0 + j;
+        if (i < N) {
+            const float4 s = ring[(lrow0 + i) % ring_cap];
+            const float delta = (i + 1 < N) ? (__ldg(z + i + 1) - __ldg(z + i)) : 1e10f;
+            const float alpha = 1.f - expf(-s.x * delta);
+            T_local *= (1.f - alpha + 1e-10f);
+        }
+    }
+    float T = warp_excl_prod_f(T_local, lane);
+    float cr = 0.f, cg = 0.f, cb = 0.f, d = 0.f, ws = 0.f;
+    for (int j = 0; j < per; ++j) {
+        const int i = i0 + j;
+        if (i < N) {
+            const float4 s = ring[(lrow0 + i) % ring_cap];
+            const float zi = __ldg(z + i);
+            const float delta = (i + 1 < N) ? (__ldg(z + i + 1) - zi) : 1e10f;
+            const float alpha = 1.f - expf(-s.x * delta);
+            const float w = alpha * T;
+            cr += w * s.y; cg += w * s.z; cb += w * s.w;
+            d += w * zi; ws += w;
+            T *= (1.f - alpha + 1e-10f);
+        }
+    }
+    cr = warp_sum_f(cr); cg = warp_sum_f(cg); cb = warp_sum_f(cb); d = warp_sum_f(d); ws = warp_sum_f(ws);
+    if (lane == 0) {
+        if (p.white_bg) { cr = cr + 1.f - ws; cg = cg + 1.f - ws; cb = cb + 1.f - ws; }
+        p.rgb[gray * 3 + 0] = cr; p.rgb[gray * 3 + 1] = cg; p.rgb[gray * 3 + 2] = cb;
+        p.depth[gray] = d;
+        if (p.acc) p.acc[gray] = ws;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constant__ FwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA0 = smem;
+    uint8_t* sW = smem + 2 * kATile;
+    float4* sRing = (float4*)(sW + kNumStages * kSlot);
+    uint64_t* bars = (uint64_t*)((uint8_t*)sRing + (size_t)p.ring_cap * 16);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = bars + kNumStages;
+    uint64_t* a_ready = bars + 2 * kNumStages;
+    uint64_t* acc_full = a_ready + 2;
+    uint32_t* tmem_slot = (uint32_t*)(acc_full + 2);
+    volatile int* final_count = (volatile int*)(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nl = p.n_layers;
+
+    // ---- this CTA's contiguous share of the work -------------------------------------------
+    int64_t row0, nrows, ray0 = 0;
+    if (p.mode == 0) {
+        const int64_t base = p.n_rays / gridDim.x, rem = p.n_rays % gridDim.x;
+        ray0 = (int64_t)blockIdx.x * base + min((int64_t)blockIdx.x, rem);
+        const int64_t nr = base + ((int64_t)blockIdx.x < rem ? 1 : 0);
+        row0 = ray0 * p.rs.N; nrows = nr * p.rs.N;
+    } else {
+        const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
+        const int64_t base = tiles / gridDim.x, rem = tiles % gridDim.x;
+        const int64_t t0 = (int64_t)blockIdx.x * base + min((int64_t)blockIdx.x, rem);
+        const int64_t nt = base + ((int64_t)blockIdx.x < rem ? 1 : 0);
+        row0 = t0 * kTileRows;
+        nrows = min(p.S - row0, nt * kTileRows);
+        if (nrows < 0) nrows = 0;
+    }
+    const int T = (int)((nrows + kTileRows - 1) / kTileRows);
+    const int rounds = (T + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], 1); }
+        for (int g = 0; g < 2; ++g) { umma::mbar_init(&a_ready[g], 4); umma::mbar_init(&acc_full[g], 1); }
+        final_count[0] = 0; final_count[1] = 0;
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== weight producer: TMA-engine bulk copies of stage images into the ring =====
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int r = 0; r < rounds; ++r)
+                for (int l = 0; l < nl; ++l)
+                    for (int g = 0; g < 2; ++g) {
+                        if (2 * r + g >= T) continue;
+                        const FwdLayer& L = p.layers[l];
+                        const int n_main = L.n_kchunks * L.n_halves;
+                        const int nst = n_main + (L.has_dir ? L.n_halves : 0);
+                        for (int s = 0; s < nst; ++s) {
+                            umma::mbar_wait(&w_empty[stage], ph ^ 1);
+                            const uint32_t bytes = s < n_main ? kSlot : kSlot / 2;
+                            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
+                            umma::bulk_g2s(sW + stage * kSlot, p.packed + L.w_off + (size_t)s * kSlot, bytes,
+                                           &w_full[stage]);
+                            if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread drives the tensor core for both tiles =====
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            const uint32_t idesc = umma::make_idesc(128, 128, 0, 0);
+            for (int r = 0; r < rounds; ++r)
+                for (int l = 0; l < nl; ++l)
+                    for (int g = 0; g < 2; ++g) {
+                        if (2 * r + g >= T) continue;
+                        const FwdLayer& L = p.layers[l];
+                        umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
+                        umma::tc_fence_after();
+                        const uint32_t a_base = umma::smem_u32(sA0 + g * kATile);
+                        const uint32_t d_base = tmem + (uint32_t)g * 256u;
+                        for (int c = 0; c < L.n_kchunks; ++c)
+                            for (int h = 0; h < L.n_halves; ++h) {
+                                umma::mbar_wait(&w_full[stage], ph);
+                                umma::tc_fence_after();
+                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint64_t da = umma::make_sdesc(a_base + c * kABlock + ks * 32, 16, 1024, umma::SWZ_128B);
+                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 1024, umma::SWZ_128B);
+                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, (c | ks) ? 1u : 0u);
+                                }
+                                umma::mma_commit(&w_empty[stage]);
+                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+                            }
+                        if (L.has_dir)
+                            for (int h = 0; h < L.n_halves; ++h) {
+                                umma::mbar_wait(&w_full[stage], ph);
+                                umma::tc_fence_after();
+                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
+#pragma unroll
+                                for (int ks = 0; ks < 2; ++ks) {
+                                    const uint64_t da = umma::make_sdesc(a_base + 4 * kABlock + ks * 32, 16, 512, umma::SWZ_64B);
+                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 512, umma::SWZ_64B);
+                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, 1u);
+                                }
+                                umma::mma_commit(&w_empty[stage]);
+                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+                            }
+                        umma::mma_commit(&acc_full[g]);
+                    }
+        }
+    } else {
+        // ===== compute groups: PE, per-layer epilogues (TMEM -> bias/ReLU -> bf16 operand), heads, compositing =====
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;                  // TMEM lane quarter this warp may access
+        const int wi = (warp - 2) & 3;
+        const int row = q * 32 + lane;
+        uint8_t* sA = sA0 + g * kATile;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+        const int N = p.rs.N;
+        for (int r = 0; r < rounds; ++r) {
+            const int t = 2 * r + g;
+            if (t >= T) break;
+            const int64_t lrow = (int64_t)t * kTileRows + row;
+            const bool valid = lrow < nrows;
+            const int64_t grow = row0 + lrow;
+            // ---- inputs: sample position and view direction of this row ----
+            float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+            if (valid) {
+                if (p.mode == 0) {
+                    const int64_t ray = grow / N;
+                    const int zi = (int)(grow - ray * N);
+                    float o[3];
+                    cnb_fetch_ray(p.rs, ray, o, dir);
+                    const int64_t seg = ray / p.rs.rays_per_segment;
+                    const float z = __ldg(p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0) + zi);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + grow * 3 + k); dir[k] = __ldg(p.viewdir + grow * 3 + k); }
+                }
+            }
+            int64_t code = 0;
+            if (p.n_codes > 1) { code = (valid ? grow : row0) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+            encode_row(pos, dir, valid, sA, sA + 4 * kABlock, row);
+            umma::tc_fence_before();
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&a_ready[g]);
+
+            float sig_pre = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            for (int l = 0; l < nl; ++l) {
+                const FwdLayer& L = p.layers[l];
+                umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u);
+                umma::tc_fence_after();
+                const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
+                const int ncc = L.n_halves * 4;
+                const bool store = (l + 1 < nl);
+                for (int cc = 0; cc < ncc; ++cc) {
+                    uint32_t rr[32];
+                    umma::tmem_ld32(taddr + cc * 32, rr);
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const int col = cc * 32 + j8 * 8;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                        float v[8];
+                        v[0] = __uint_as_float(rr[j8 * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[j8 * 8 + 1]) + b0.y;
+                        v[2] = __uint_as_float(rr[j8 * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[j8 * 8 + 3]) + b0.w;
+                        v[4] = __uint_as_float(rr[j8 * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[j8 * 8 + 5]) + b1.y;
+                        v[6] = __uint_as_float(rr[j8 * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[j8 * 8 + 7]) + b1.w;
+                        if (L.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                        }
+                        if (L.kind == 1) {          // sigma head on the fp32 feature (src/model.py:45)
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col + 4));
+                            sig_pre = fmaf(v[0], w0.x, sig_pre); sig_pre = fmaf(v[1], w0.y, sig_pre);
+                            sig_pre = fmaf(v[2], w0.z, sig_pre); sig_pre = fmaf(v[3], w0.w, sig_pre);
+                            sig_pre = fmaf(v[4], w1.x, sig_pre); sig_pre = fmaf(v[5], w1.y, sig_pre);
+                            sig_pre = fmaf(v[6], w1.z, sig_pre); sig_pre = fmaf(v[7], w1.w, sig_pre);
+                        } else if (L.kind == 2) {   // rgb.2 on the fp32 hidden (src/model.py:52)
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                cr = fmaf(v[i], __ldg(p.w_rgb2 + col + i), cr);
+                                cg = fmaf(v[i], __ldg(p.w_rgb2 + (kW / 2) + col + i), cg);
+                                cb = fmaf(v[i], __ldg(p.w_rgb2 + kW + col + i), cb);
+                            }
+                        }
+                        if (store) {
+                            const int blk = cc >> 1, chunk = ((cc & 1) << 2) + j8;
+                            st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4),
+                                         umma::pack_bf16(v[0], v[1]), umma::pack_bf16(v[2], v[3]),
+                                         umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
+                        }
+                    }
+                }
+                if (store) {
+                    umma::tc_fence_before();
+                    umma::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&a_ready[g]);
+                }
+            }
+            // ---- heads -> outputs ----
+            const float sigma = cnb_softplus(sig_pre + __ldg(p.b_sigma));
+            cr += __ldg(p.b_rgb2 + 0); cg += __ldg(p.b_rgb2 + 1); cb += __ldg(p.b_rgb2 + 2);
+            if (p.mode == 1) {
+                if (valid) {
+                    p.sigmas[grow] = sigma;
+                    p.rgbs[grow * 3 + 0] = cr; p.rgbs[grow * 3 + 1] = cg; p.rgbs[grow * 3 + 2] = cb;
+                }
+                continue;
+            }
+            const float4 smp = make_float4(sigma, cr, cg, cb);
+            if (valid) {
+                sRing[lrow % p.ring_cap] = smp;
+                if (p.samples_out) p.samples_out[grow] = smp;
+            }
+            umma::named_bar_sync(1 + g, 128);
+            if (row == 0) { __threadfence_block(); final_count[g] = r + 1; }
+            {   // rays ending in this tile may have begun in the other group's previous tile
+                const int need = (g == 1) ? r + 1 : r;
+                const long long t0 = clock64();
+                while (final_count[g ^ 1] < need) {
+                    if (clock64() - t0 > 2000000000LL) { atomicExch(&umma::g_umma_timeout, 2u); break; }
+                }
+                __threadfence_block();
+            }
+            const int64_t tile_lo = (int64_t)t * kTileRows, tile_hi = min(tile_lo + kTileRows, nrows);
+            const int64_t q_first = tile_lo / N;        // first ray whose last row lies in this tile
+            const int64_t q_last = tile_hi / N - 1;     // last ray completed by the end of this tile
+            for (int64_t qr = q_first + wi; qr <= q_last; qr += 4)
+                composite_ray(p, sRing, p.ring_cap, qr * N, ray0 + qr, lane);
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Weight packing: fp32 parameter matrices -> bf16 stage images in the exact shared-memory
+// byte layout the UMMA descriptors expect (so a stage is one linear bulk copy).
+struct PackArgs {
+    const float* W; int ld;          // source matrix, row stride
+    int n_total, k_total;            // valid extents of the operand's N (rows) and K (cols)
+    int transpose;                   // 0: B[n][k] = W[n*ld + k];  1: B[n][k] = W[k*ld + n]  (dgrad)
+    int n_kchunks, n_halves, has_dir;
+    int dir_k0, dir_width;           // K range of the PE(viewdir) columns inside W
+    uint8_t* dst;
+};
+
+__global__ void k_pack_layer(PackArgs a) {
+    const int s = blockIdx.x;
+    const int n_main = a.n_kchunks * a.n_halves;
+    uint8_t* out = a.dst + (size_t)s * kSlot;
+    if (s < n_main) {
+        const int c = s / a.n_halves, h = s % a.n_halves;
+        for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
+            const int rown = i >> 3, ch = i & 7;
+            const int n = h * 128 + rown;
+            uint32_t w[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                float f[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int k = c * 64 + ch * 8 + e2 * 2 + e;
+                    f[e] = (n < a.n_total && k < a.k_total)
+                               ? (a.transpose ? a.W[(size_t)k * a.ld + n] : a.W[(size_t)n * a.ld + k]) : 0.f;
+                }
+                w[e2] = umma::pack_bf16(f[0], f[1]);
+            }
+            *reinterpret_cast<uint4*>(out + rown * 128 + ((ch ^ (rown & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    } else {
+        const int h = s - n_main;
+        for (int i = threadIdx.x; i < 128 * 4; i += blockDim.x) {
+            const int rown = i >> 2, ch = i & 3;
+            const int n = h * 128 + rown;
+            uint32_t w[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+                float f[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int j = ch * 8 + e2 * 2 + e;
+                    f[e] = (n < a.n_total && j < a.dir_width) ? a.W[(size_t)n * a.ld + a.dir_k0 + j] : 0.f;
+                }
+                w[e2] = umma::pack_bf16(f[0], f[1]);
+            }
+            *reinterpret_cast<uint4*>(out + rown * 64 + ((ch ^ ((rown >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// folded[code][j][n] = b_j[n] + sum_k W_j[n][k] z_j[code][k]   (the y + z add of src/model.py:42,50
+// moved across the linear layer: (y + z) W^T + b = y W^T + (W z + b)).  One warp per output.
+__global__ void k_fold_bias(const float* __restrict__ Wj, const float* __restrict__ bj, const float* __restrict__ z,
+                            int64_t ldz, int n_codes, float* __restrict__ out, int64_t ldo) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (gw >= n_codes * kW) return;
+    const int o = gw / kW, n = gw - o * kW;
+    float acc = 0.f;
+    for (int i = lane; i < kW; i += 32) acc = fmaf(__ldg(Wj + (size_t)n * kW + i), z[(size_t)o * ldz + i], acc);
+    acc = warp_sum_f(acc);
+    if (lane == 0) out[(size_t)o * ldo + n] = acc + __ldg(bj + n);
+}
+
+// ---------------------------------------------------------------------------
+struct Plan {
+    int n_layers, n_folded;
+    FwdLayer fwd[kMaxLayers];
+    size_t fwd_bytes, total_bytes;
+};
+
+int make_plan(const cnb_net_config* c, const float* const* P, Plan* pl) {
+    if (c->W != kW || c->num_xyz_freq != kLx || c->num_dir_freq != kLd) return CNB_E_UNSUPPORTED;
+    CnbLayout L; cnb_make_layout(c, &L);
+    int n = 0, nf = 0; size_t off = 0;
+    auto add = [&](int wi, int kch, int dir, int halves, int relu, int kind, int folded) {
+        FwdLayer f = {};
+        f.w_off = (uint32_t)off; f.n_kchunks = (uint8_t)kch; f.has_dir = (uint8_t)dir; f.n_halves = (uint8_t)halves;
+        f.relu = (uint8_t)relu; f.kind = (uint8_t)kind; f.folded = (int8_t)folded;
+        f.bias = P ? P[wi + 1] : nullptr;
+        off += (size_t)(kch + dir) * halves * kSlot;
+        pl->fwd[n++] = f;
+    };
+    add(L.i_enc_xyz, 1, 0, 2, 1, 0, -1);
+    for (int j = 0; j < c->shape_blocks; ++j) add(L.i_s[j], 4, 0, 2, 1, 0, nf++);
+    add(L.i_enc_shape, 4, 0, 2, 0, 1, -1);
+    add(L.i_enc_vd, 4, 1, 2, 1, 0, -1);
+    for (int j = 0; j < c->texture_blocks; ++j) add(L.i_t[j], 4, 0, 2, 1, 0, nf++);
+    add(L.i_rgb0, 4, 0, 1, 1, 2, -1);
+    pl->n_layers = n; pl->n_folded = nf; pl->fwd_bytes = off; pl->total_bytes = off;
+    return CNB_OK;
+}
+
+struct FwdWorkspace { float *z, *folded; float4* samples; size_t bytes; };
+
+size_t carve_fwd(const cnb_net_config* c, int n_codes, int64_t spill_samples, char* base, FwdWorkspace* w) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
+    const int nf = c->shape_blocks + c->texture_blocks;
+    FwdWorkspace x = {};
+    x.z = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    x.folded = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    x.samples = (float4*)take(sizeof(float4) * (size_t)spill_samples);
+    x.bytes = off;
+    if (w) *w = x;
+    return off;
+}
+
+// z_j = ReLU(latent layer_j(code)) and the folded per-code biases.
+int latent_and_fold(const cnb_net_config* c, const float* const* P, const float* shape_codes, const float* tex_codes,
+                    int n_codes, FwdWorkspace& w, cudaStream_t st) {
+    CnbLayout L; cnb_make_layout(c, &L);
+    const int nf = c->shape_blocks + c->texture_blocks;
+    const int64_t ld = (int64_t)nf * kW;
+    const int threads = 256, blocks = (n_codes * kW * 32 + threads - 1) / threads;
+    for (int j = 0; j < nf; ++j) {
+        const bool shape = j < c->shape_blocks;
+        const int jj = shape ? j : j - c->shape_blocks;
+        const int il = shape ? L.i_sl[jj] : L.i_tl[jj];
+        const int iw = shape ? L.i_s[jj] : L.i_t[jj];
+        CNB_TRY(cnb_launch_latent_fwd(P[il], P[il + 1], shape ? shape_codes : tex_codes, n_codes, c->latent_dim, kW,
+                                      w.z + (size_t)j * kW, ld, st));
+        k_fold_bias<<<blocks, threads, 0, st>>>(P[iw], P[iw + 1], w.z + (size_t)j * kW, ld, n_codes,
+                                               w.folded + (size_t)j * kW, ld);
+        CNB_LAUNCH_CHECK();
+    }
+    return CNB_OK;
+}
+
+int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packed, const Plan& pl, FwdParams& fp,
+               int64_t total_rows, cudaStream_t st) {
+    CnbLayout L; cnb_make_layout(c, &L);
+    fp.n_layers = pl.n_layers;
+    for (int i = 0; i < pl.n_layers; ++i) fp.layers[i] = pl.fwd[i];
+    fp.packed = (const uint8_t*)packed;
+    fp.n_folded = pl.n_folded;
+    fp.w_sigma = P[L.i_sigma]; fp.b_sigma = P[L.i_sigma + 1];
+    fp.w_rgb2 = P[L.i_rgb2]; fp.b_rgb2 = P[L.i_rgb2 + 1];
+    const int N = fp.mode == 0 ? fp.rs.N : 1;
+    fp.ring_cap = fp.mode == 0 ? N + 384 : 16;
+    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + (size_t)fp.ring_cap * 16 + 256;
+    if (smem > 232448) return CNB_E_UNSUPPORTED;
+    int dev = 0, sms = 0;
+    CNB_CUDA_TRY(cudaGetDevice(&dev));
+    CNB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    int64_t units = (total_rows + 2 * kTileRows - 1) / (2 * kTileRows);
+    if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
+    int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
+    CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_render_fwd<<<grid, kThreads, smem, st>>>(fp);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+size_t cnb_sm100_packed_bytes(const cnb_net_config* cfg) {
+    Plan pl;
+    if (make_plan(cfg, nullptr, &pl) != CNB_OK) return 256;   // fp32-only network shapes need no packed copy
+    return pl.total_bytes + 1024;
+}
+
+int cnb_sm100_pack_weights(const cnb_net_config* cfg, const float* const* P, void* packed, cudaStream_t st) {
+    Plan pl;
+    const int rc = make_plan(cfg, P, &pl);
+    if (rc == CNB_E_UNSUPPORTED) return CNB_OK;      // nothing to pack; the bf16 entry points will refuse
+    CNB_TRY(rc);
+    if (((uintptr_t)packed & 127) != 0) return CNB_E_ALIGNMENT;
+    CnbLayout L; cnb_make_layout(cfg, &L);
+    int li = 0;
+    auto pack = [&](int wi, int ld, int n_total, int k_total, int dir_k0, int dir_w) -> int {
+        const FwdLayer& f = pl.fwd[li++];
+        PackArgs a = {};
+        a.W = P[wi]; a.ld = ld; a.n_total = n_total; a.k_total = k_total; a.transpose = 0;
+        a.n_kchunks = f.n_kchunks; a.n_halves = f.n_halves; a.has_dir = f.has_dir; a.dir_k0 = dir_k0; a.dir_width = dir_w;
+        a.dst = (uint8_t*)packed + f.w_off;
+        const int nst = (f.n_kchunks + f.has_dir) * f.n_halves;
+        k_pack_layer<<<nst, 256, 0, st>>>(a);
+        CNB_LAUNCH_CHECK();
+        return CNB_OK;
+    };
+    CNB_TRY(pack(L.i_enc_xyz, L.d_xyz, kW, L.d_xyz, 0, 0));
+    for (int j = 0; j < cfg->shape_blocks; ++j) CNB_TRY(pack(L.i_s[j], kW, kW, kW, 0, 0));
+    CNB_TRY(pack(L.i_enc_shape, kW, kW, kW, 0, 0));
+    CNB_TRY(pack(L.i_enc_vd, kW + L.d_dir, kW, kW, kW, L.d_dir));
+    for (int j = 0; j < cfg->texture_blocks; ++j) CNB_TRY(pack(L.i_t[j], kW, kW, kW, 0, 0));
+    CNB_TRY(pack(L.i_rgb0, kW, kW / 2, kW, 0, 0));
+    return CNB_OK;
+}
+
+size_t cnb_sm100_mlp_workspace_bytes(const cnb_net_config* cfg, int64_t S, int n_codes, int backward) {
+    (void)S; (void)backward;
+    return carve_fwd(cfg, n_codes, 0, nullptr, nullptr) + 256;
+}
+
+size_t cnb_sm100_render_workspace_bytes(const cnb_net_config* cfg, const cnb_ray_batch* rays, int backward) {
+    return carve_fwd(cfg, rays->n_codes, backward ? rays->n_rays * rays->n_samples : 0, nullptr, nullptr) + 256;
+}
+
+int cnb_sm100_mlp_forward(const cnb_net_config* cfg, const float* const* P, const void* packed, const float* xyz,
+                          const float* viewdir, const float* shape_codes, const float* tex_codes, int n_codes,
+                          int64_t samples_per_code, int64_t S, float* sigmas, float* rgbs, void* ws, size_t ws_bytes,
+                          cudaStream_t st) {
+    Plan pl;
+    CNB_TRY(make_plan(cfg, P, &pl));
+    if (n_codes > 1 && (samples_per_code % 32) != 0) return CNB_E_UNSUPPORTED;
+    FwdWorkspace w;
+    if (!ws || ws_bytes < carve_fwd(cfg, n_codes, 0, nullptr, nullptr)) return CNB_E_WORKSPACE;
+    if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
+    carve_fwd(cfg, n_codes, 0, (char*)ws, &w);
+    CNB_TRY(latent_and_fold(cfg, P, shape_codes, tex_codes, n_codes, w, st));
+    FwdParams fp = {};
+    fp.mode = 1; fp.xyz = xyz; fp.viewdir = viewdir; fp.S = S; fp.n_rays = 0;
+    fp.folded = w.folded; fp.n_codes = n_codes; fp.rows_per_code = samples_per_code > 0 ? samples_per_code : S;
+    fp.sigmas = sigmas; fp.rgbs = rgbs;
+    fp.rs.N = 1;
+    return launch_fwd(cfg, P, packed, pl, fp, S, st);
+}
+
+int cnb_sm100_mlp_backward(const cnb_net_config*, const float* const*, const void*, const float*, const float*,
+                           const float*, const float*, int, int64_t, int64_t, const float*, const float*, float*,
+                           float*, float*, void*, size_t, cudaStream_t) {
+    return CNB_E_UNSUPPORTED;
+}
+
+int cnb_sm100_render(const cnb_net_config* cfg, const float* const* P, const void* packed, const cnb_ray_batch* rays,
+                     int mode, const float* d_rgb, const float* d_depth, const float* target, float loss_scale,
+                     float* rgb, float* depth, float* acc, float* sq_err, float* d_params, float* d_shape,
+                     float* d_tex, void* ws, size_t ws_bytes, cudaStream_t st) {
+    (void)d_rgb; (void)d_depth; (void)target; (void)loss_scale; (void)sq_err; (void)d_params; (void)d_shape; (void)d_tex;
+    Plan pl;
+    CNB_TRY(make_plan(cfg, P, &pl));
+    if (mode != 0) return CNB_E_UNSUPPORTED;
+    const int N = rays->n_samples;
+    if (N > 512) return CNB_E_UNSUPPORTED;
+    const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * N;
+    if (rays->n_codes > 1 && (rows_per_code % 32) != 0) return CNB_E_UNSUPPORTED;
+    FwdWorkspace w;
+    if (!ws || ws_bytes < carve_fwd(cfg, rays->n_codes, 0, nullptr, nullptr)) return CNB_E_WORKSPACE;
+    if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
+    carve_fwd(cfg, rays->n_codes, 0, (char*)ws, &w);
+    CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w, st));
+    FwdParams fp = {};
+    fp.mode = 0; fp.rs = cnb_make_ray_source(rays); fp.n_rays = rays->n_rays; fp.S = rays->n_rays * N;
+    fp.folded = w.folded; fp.n_codes = rays->n_codes; fp.rows_per_code = rays->n_codes > 1 ? rows_per_code : fp.S;
+    fp.white_bg = rays->white_bg;
+    fp.rgb = rgb; fp.depth = depth; fp.acc = acc;
+    return launch_fwd(cfg, P, packed, pl, fp, fp.S, st);
+}
+
+int cnb_sm100_pipeline_timeouts(void) {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, umma::g_umma_timeout, sizeof(unsigned int)) != cudaSuccess) return -1;
+    return (int)v;
+}

@@ -20,3 +20,5 @@ int cnb_sm100_render(const cnb_net_config* cfg, const float* const* params, cons
                      const cnb_ray_batch* rays, int mode, const float* d_rgb, const float* d_depth,
                      const float* target, float loss_scale, float* rgb, float* depth, float* acc, float* sq_err,
                      float* d_params, float* d_shape, float* d_tex, void* ws, size_t ws_bytes, cudaStream_t st);
+// debug: non-zero if any mbarrier wait inside the tensor-core kernels ever timed out (synchronises the device)
+int cnb_sm100_pipeline_timeouts(void);

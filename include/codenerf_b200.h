@@ -168,6 +168,10 @@ int cnb_render_train_step(const cnb_net_config* cfg, const float* const* params,
                           float* d_params, float* d_shape_codes, float* d_texture_codes,
                           void* workspace, size_t workspace_bytes, cnb_stream_t stream);
 
+/* Debug aid: synchronises the device and returns non-zero if a pipeline wait inside the
+ * tensor-core kernels ever hit its watchdog (a protocol bug; results are then invalid). */
+int cnb_debug_pipeline_timeouts(void);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 int64_t cnb_launch_count(void);
 

@@ -1,0 +1,115 @@
+"""bf16 tensor-core path (tcgen05 / TMEM kernels) against the oracle.
+Tolerance: rgb / depth / acc within 1e-2 absolute (BASELINE.json north_star, bf16 mode)."""
+import numpy as np
+import pytest
+import torch
+
+from codenerf_b200 import synthetic as syn
+from oracle import oracle as orc
+from tests import golden_util as gu
+from tests import gpu_util as U
+
+G_REN, REN_CASES = gu.render_meta()
+ATOL = 1e-2
+
+
+def _no_timeouts():
+    from codenerf_b200 import _lib
+    assert _lib.load().cnb_debug_pipeline_timeouts() == 0, "a tensor-core pipeline wait timed out"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", REN_CASES, ids=lambda c: f"r{c['k']}")
+def test_unfused_forward_bf16_vs_reference_fixture(c):
+    import codenerf_b200 as cn
+    k = c["k"]
+    inp = gu.render_case_inputs(c)
+    z = G_REN[f"r{k}_z"].view(np.float32)
+    ro, vd = orc.get_rays(c["H"], c["W"], inp["focal"], inp["c2w"], True)
+    xyz, vdr = orc.sample_from_rays(ro, vd, z)
+    model, flat = U.make_model("bf16")
+    R, N = inp["R"], c["N"]
+    sc = torch.from_numpy(inp["shape_codes"]).cuda()
+    tc = torch.from_numpy(inp["tex_codes"]).cuda()
+    if c["n_codes"] > 1:
+        per = R // c["n_codes"]
+        sc = sc.repeat_interleave(per, 0).unsqueeze(1)
+        tc = tc.repeat_interleave(per, 0).unsqueeze(1)
+    with torch.no_grad():
+        sig, col = model(torch.from_numpy(xyz).cuda(), torch.from_numpy(vdr).cuda(), sc, tc)
+    _no_timeouts()
+    sig_ref, col_ref = G_REN[f"r{k}_sigmas"], G_REN[f"r{k}_rgbs"]
+    e_s = np.abs(sig.cpu().numpy().reshape(R, N) - sig_ref).max()
+    e_c = np.abs(col.cpu().numpy() - col_ref).max()
+    print(f"case r{k}: max|dsigma|={e_s:.3e} (max {np.abs(sig_ref).max():.3f})  max|drgb|={e_c:.3e} (max {np.abs(col_ref).max():.3f})")
+    assert e_s < 2e-2 * max(1.0, np.abs(sig_ref).max())
+    assert e_c < 2e-2 * max(1.0, np.abs(col_ref).max())
+    rgb, depth, acc = cn.volume_rendering_with_acc(sig, col, torch.from_numpy(z).cuda(), white_bg=c["white"])
+    np.testing.assert_allclose(rgb.cpu().numpy(), G_REN[f"r{k}_rgb"], atol=ATOL, rtol=0)
+    np.testing.assert_allclose(depth.cpu().numpy(), G_REN[f"r{k}_depth"], atol=ATOL, rtol=0)
+    np.testing.assert_allclose(acc.cpu().numpy(), G_REN[f"r{k}_acc"], atol=ATOL, rtol=0)
+
+
+def _fused_case(N, H, W, n_seg, ray_count, cat, explicit_rays=False, n_codes=None):
+    import codenerf_b200 as cn
+    model, flat = U.make_model("bf16")
+    focal = 131.25 * W / 128.0
+    c2ws = np.stack([syn.look_at_pose(700 + g, cat["radius"]) for g in range(n_seg)])
+    zs = np.stack([orc.z_vals(cat["near"], cat["far"], N, orc.torch_rand(4000 + g, N)) for g in range(n_seg)])
+    pix = np.array([(37 * g) % (H * W - ray_count + 1) for g in range(n_seg)], np.int32)
+    nc = n_seg if n_codes is None else n_codes
+    scodes, tcodes = syn.make_codes(11, nc), syn.make_codes(12, nc)
+    code_of = (lambda g: g) if nc == n_seg else (lambda g: 0)
+    ref = [orc.render(flat, H, W, focal, c2ws[g], zs[g], scodes[code_of(g):code_of(g) + 1],
+                      tcodes[code_of(g):code_of(g) + 1], True, ray_begin=int(pix[g]), ray_count=ray_count)
+           for g in range(n_seg)]
+    if explicit_rays:
+        ros, vds = [], []
+        for g in range(n_seg):
+            ro, vd = orc.get_rays(H, W, focal, c2ws[g], True)
+            ros.append(ro[pix[g]:pix[g] + ray_count])
+            vds.append(vd[pix[g]:pix[g] + ray_count])
+        bundle = cn.RayBundle(z_vals=torch.from_numpy(zs).cuda(), rays_per_segment=ray_count,
+                              rays_o=torch.from_numpy(np.concatenate(ros)).cuda(),
+                              viewdirs=torch.from_numpy(np.concatenate(vds)).cuda())
+    else:
+        bundle = cn.RayBundle(z_vals=torch.from_numpy(zs).cuda(), rays_per_segment=ray_count,
+                              c2w=torch.from_numpy(c2ws).cuda(), pix_begin=torch.from_numpy(pix).cuda(),
+                              focal=torch.tensor([focal], dtype=torch.float64), H=H, W=W)
+    return model, flat, bundle, scodes, tcodes, zs, ref
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W,n_seg,ray_count,cat,explicit", [
+    (64, 32, 32, 3, 128, syn.SRN_CARS, False),
+    (64, 128, 128, 2, 2048, syn.SRN_CARS, False),      # the reference's chunk size (train.py:17)
+    (96, 24, 40, 2, 100, syn.SRN_CHAIRS, False),       # N = 96 (jsonfiles/*.json): rays straddle tiles
+    (40, 16, 16, 1, 77, syn.SRN_CARS, True),           # ragged everything, rays from memory
+    (128, 16, 16, 4, 16, syn.SRN_CHAIRS, True),
+    (200, 16, 16, 1, 7, syn.SRN_CARS, False),          # a ray longer than a tile
+])
+def test_fused_forward_bf16_vs_oracle(N, H, W, n_seg, ray_count, cat, explicit):
+    import codenerf_b200 as cn
+    model, flat, bundle, scodes, tcodes, zs, ref = _fused_case(N, H, W, n_seg, ray_count, cat, explicit)
+    with torch.no_grad():
+        rgb, depth, acc = cn.render(model, bundle, torch.from_numpy(scodes).cuda(), torch.from_numpy(tcodes).cuda())
+    _no_timeouts()
+    rgb_ref = np.concatenate([r["rgb"] for r in ref])
+    d_ref = np.concatenate([r["depth"] for r in ref])
+    a_ref = np.concatenate([r["acc"] for r in ref])
+    print("max err rgb %.3e depth %.3e acc %.3e" % (np.abs(rgb.cpu().numpy() - rgb_ref).max(),
+                                                  np.abs(depth.cpu().numpy() - d_ref).max(),
+                                                  np.abs(acc.cpu().numpy() - a_ref).max()))
+    np.testing.assert_allclose(rgb.cpu().numpy(), rgb_ref, atol=ATOL, rtol=0)
+    np.testing.assert_allclose(depth.cpu().numpy(), d_ref, atol=ATOL, rtol=0)
+    np.testing.assert_allclose(acc.cpu().numpy(), a_ref, atol=ATOL, rtol=0)
+
+
+@pytest.mark.gpu
+def test_fused_forward_bf16_broadcast_code_many_segments():
+    import codenerf_b200 as cn
+    model, flat, bundle, scodes, tcodes, zs, ref = _fused_case(64, 32, 32, 5, 64, syn.SRN_CARS, False, n_codes=1)
+    with torch.no_grad():
+        rgb, depth, acc = cn.render(model, bundle, torch.from_numpy(scodes).cuda(), torch.from_numpy(tcodes).cuda())
+    _no_timeouts()
+    np.testing.assert_allclose(rgb.cpu().numpy(), np.concatenate([r["rgb"] for r in ref]), atol=ATOL, rtol=0)
