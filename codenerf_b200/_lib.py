@@ -50,6 +50,7 @@ EXPORTS = [
     "cnb_volume_rendering_backward", "cnb_packed_weights_bytes", "cnb_pack_weights", "cnb_mlp_workspace_bytes",
     "cnb_mlp_forward", "cnb_mlp_backward", "cnb_render_workspace_bytes", "cnb_render_forward",
     "cnb_render_backward", "cnb_render_train_step", "cnb_launch_count", "cnb_debug_pipeline_timeouts",
+    "cnb_profile_enable", "cnb_profile_read",
 ]
 
 _lib = None
@@ -109,6 +110,10 @@ def load():
                                         vp, sz, vp]
     L.cnb_launch_count.restype = i64
     L.cnb_debug_pipeline_timeouts.restype = i32
+    L.cnb_profile_enable.restype = i32
+    L.cnb_profile_enable.argtypes = [i32]
+    L.cnb_profile_read.restype = i32
+    L.cnb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), i32]
     _lib = L
     return L
 

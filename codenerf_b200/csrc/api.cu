@@ -24,6 +24,47 @@ extern "C" const char* cnb_strerror(int status) {
     return "codenerf_b200: unknown status";
 }
 
+// ---- kernel timing aid --------------------------------------------------------------------
+namespace {
+constexpr int kProfCap = 512;
+struct ProfState {
+    bool on = false;
+    cudaEvent_t ev[CNB_K_COUNT][kProfCap][2];
+    bool made[CNB_K_COUNT][kProfCap] = {};
+    int n[CNB_K_COUNT] = {};
+} g_prof;
+}  // namespace
+
+void cnb_prof_begin(int k, cudaStream_t st) {
+    if (!g_prof.on || g_prof.n[k] >= kProfCap) return;
+    const int i = g_prof.n[k];
+    if (!g_prof.made[k][i]) {
+        cudaEventCreate(&g_prof.ev[k][i][0]); cudaEventCreate(&g_prof.ev[k][i][1]);
+        g_prof.made[k][i] = true;
+    }
+    cudaEventRecord(g_prof.ev[k][i][0], st);
+}
+void cnb_prof_end(int k, cudaStream_t st) {
+    if (!g_prof.on || g_prof.n[k] >= kProfCap) return;
+    cudaEventRecord(g_prof.ev[k][g_prof.n[k]][1], st);
+    g_prof.n[k]++;
+}
+extern "C" int cnb_profile_enable(int on) {
+    g_prof.on = on != 0;
+    for (int k = 0; k < CNB_K_COUNT; ++k) g_prof.n[k] = 0;
+    return CNB_OK;
+}
+extern "C" int cnb_profile_read(int kernel_id, float* ms, int cap) {
+    if (kernel_id < 0 || kernel_id >= CNB_K_COUNT || !ms || cap < 0) return CNB_E_INVALID;
+    int n = g_prof.n[kernel_id] < cap ? g_prof.n[kernel_id] : cap;
+    for (int i = 0; i < n; ++i) {
+        if (cudaEventSynchronize(g_prof.ev[kernel_id][i][1]) != cudaSuccess) return -1;
+        if (cudaEventElapsedTime(&ms[i], g_prof.ev[kernel_id][i][0], g_prof.ev[kernel_id][i][1]) != cudaSuccess) return -1;
+    }
+    g_prof.n[kernel_id] = 0;
+    return n;
+}
+
 extern "C" int cnb_debug_pipeline_timeouts(void) { return cnb_sm100_pipeline_timeouts(); }
 
 extern "C" int cnb_check_device(void) {
@@ -93,7 +134,12 @@ extern "C" size_t cnb_mlp_workspace_bytes(const cnb_net_config* cfg, int64_t S, 
                                           int backward) {
     if (cnb_validate_config(cfg) != CNB_OK || S <= 0 || n_codes < 1) return 0;
     if (precision == CNB_PRECISION_FP32) return cnb_fp32_workspace_bytes(cfg, S, 0, n_codes, backward, 0);
-    return cnb_sm100_mlp_workspace_bytes(cfg, S, n_codes, backward);
+    size_t n = cnb_sm100_mlp_workspace_bytes(cfg, S, n_codes, backward);
+    if (backward && !cnb_sm100_has_backward()) {
+        const size_t m = cnb_fp32_workspace_bytes(cfg, S, 0, n_codes, backward, 0);
+        if (m > n) n = m;
+    }
+    return n;
 }
 
 extern "C" int cnb_mlp_forward(const cnb_net_config* cfg, const float* const* params, const void* packed,
@@ -134,6 +180,10 @@ extern "C" int cnb_mlp_backward(const cnb_net_config* cfg, const float* const* p
                                      d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
     if (precision != CNB_PRECISION_BF16) return CNB_E_INVALID;
     if (!packed) return CNB_E_INVALID;
+    if (!cnb_sm100_has_backward())
+        return cnb_fp32_mlp_backward(cfg, params, xyz, viewdir, shape_codes, texture_codes, n_codes,
+                                     n_codes > 1 ? samples_per_code : 0, S, d_sigmas, d_rgbs, d_params, d_shape_codes,
+                                     d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
     return cnb_sm100_mlp_backward(cfg, params, packed, xyz, viewdir, shape_codes, texture_codes, n_codes,
                                   n_codes > 1 ? samples_per_code : 0, S, d_sigmas, d_rgbs, d_params, d_shape_codes,
                                   d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -145,7 +195,12 @@ extern "C" size_t cnb_render_workspace_bytes(const cnb_net_config* cfg, const cn
     if (cnb_validate_config(cfg) != CNB_OK || cnb_validate_rays(rays) != CNB_OK) return 0;
     if (precision == CNB_PRECISION_FP32)
         return cnb_fp32_workspace_bytes(cfg, rays->n_rays * rays->n_samples, rays->n_samples, rays->n_codes, backward, 1);
-    return cnb_sm100_render_workspace_bytes(cfg, rays, backward);
+    size_t n = cnb_sm100_render_workspace_bytes(cfg, rays, backward);
+    if (backward && !cnb_sm100_has_backward()) {
+        const size_t m = cnb_fp32_workspace_bytes(cfg, rays->n_rays * rays->n_samples, rays->n_samples, rays->n_codes, backward, 1);
+        if (m > n) n = m;
+    }
+    return n;
 }
 
 static int render_dispatch(const cnb_net_config* cfg, const float* const* params, const void* packed,
@@ -163,6 +218,9 @@ static int render_dispatch(const cnb_net_config* cfg, const float* const* params
                                d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
     if (precision != CNB_PRECISION_BF16) return CNB_E_INVALID;
     if (!packed) return CNB_E_INVALID;
+    if (mode != 0 && !cnb_sm100_has_backward())
+        return cnb_fp32_render(cfg, params, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc, sq_err,
+                               d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
     return cnb_sm100_render(cfg, params, packed, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc,
                             sq_err, d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
 }

@@ -31,6 +31,11 @@ extern std::atomic<long long> g_cnb_launches;
         if (_e != cudaSuccess) return (int)_e;              \
     } while (0)
 
+// Optional per-kernel CUDA-event timing (bench.py's roofline leg); no-ops unless enabled.
+enum { CNB_K_FWD = 0, CNB_K_BWD = 1, CNB_K_WGRAD = 2, CNB_K_COUNT = 3 };
+void cnb_prof_begin(int kernel_id, cudaStream_t st);
+void cnb_prof_end(int kernel_id, cudaStream_t st);
+
 // Offsets (in floats) of every parameter tensor inside the flat state_dict-ordered
 // vector -- reference src/model.py:20-34.
 struct CnbLayout {

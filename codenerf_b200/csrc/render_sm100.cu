@@ -574,7 +574,9 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
     CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cnb_prof_begin(CNB_K_FWD, st);
     k_render_fwd<<<grid, kThreads, smem, st>>>(fp);
+    cnb_prof_end(CNB_K_FWD, st);
     CNB_LAUNCH_CHECK();
     return CNB_OK;
 }
@@ -675,6 +677,8 @@ int cnb_sm100_render(const cnb_net_config* cfg, const float* const* P, const voi
     fp.rgb = rgb; fp.depth = depth; fp.acc = acc;
     return launch_fwd(cfg, P, packed, pl, fp, fp.S, st);
 }
+
+int cnb_sm100_has_backward(void) { return 0; }
 
 int cnb_sm100_pipeline_timeouts(void) {
     unsigned int v = 0;

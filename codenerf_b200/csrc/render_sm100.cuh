@@ -22,3 +22,5 @@ int cnb_sm100_render(const cnb_net_config* cfg, const float* const* params, cons
                      float* d_params, float* d_shape, float* d_tex, void* ws, size_t ws_bytes, cudaStream_t st);
 // debug: non-zero if any mbarrier wait inside the tensor-core kernels ever timed out (synchronises the device)
 int cnb_sm100_pipeline_timeouts(void);
+// 1 once the tensor-core backward kernels are in place (interim: bf16 backward runs the fp32 kernels)
+int cnb_sm100_has_backward(void);

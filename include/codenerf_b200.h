@@ -168,6 +168,14 @@ int cnb_render_train_step(const cnb_net_config* cfg, const float* const* params,
                           float* d_params, float* d_shape_codes, float* d_texture_codes,
                           void* workspace, size_t workspace_bytes, cnb_stream_t stream);
 
+/* Timing aid for bench.py's roofline leg.  When enabled the library brackets its main kernels
+ * with CUDA events on the launching stream (up to 512 launches per kernel between reads).
+ * kernel_id: 0 = fused forward, 1 = fused backward, 2 = weight-gradient GEMM.
+ * cnb_profile_read waits for the recorded launches, writes their durations in ms (launch
+ * order) and returns how many were written (< 0 on error), then clears the record. */
+int cnb_profile_enable(int on);
+int cnb_profile_read(int kernel_id, float* ms, int cap);
+
 /* Debug aid: synchronises the device and returns non-zero if a pipeline wait inside the
  * tensor-core kernels ever hit its watchdog (a protocol bug; results are then invalid). */
 int cnb_debug_pipeline_timeouts(void);
