@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcodenerf_b200.so")
-SOURCES = ["api.cu", "rays.cu", "mlp_fp32.cu", "render_sm100.cu"]
+SOURCES = ["api.cu", "rays.cu", "mlp_fp32.cu", "render_sm100.cu", "backward_sm100.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--use_fast_math=false" if False else "-Xcompiler", "-fPIC"]
 

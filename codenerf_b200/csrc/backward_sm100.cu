@@ -1,0 +1,952 @@
+// backward_sm100.cu -- CNB_PRECISION_BF16 backward of the CodeNeRF MLP on Blackwell tensor cores.
+//
+// K2  k_mlp_bwd   : per 128-row tile, recompute the forward chain (activations only ever in
+//      shared memory / TMEM, ReLU masks as bit words), then run the input-gradient chain
+//      dY_l -> dY_{l-1} = (dY_l W_l) * relu'(.) through tcgen05.mma with the transposed weight
+//      images.  Auxiliary warps reduce per-code column sums of every dY (bias and latent-code
+//      gradients) and, for training, stream the bf16 operand tiles (layer inputs A_l and
+//      pre-activation gradients dY_l) to HBM with TMA bulk stores.
+// K3  k_wgrad     : dW_l = dY_l^T A_l over all rows, a split-K tcgen05 GEMM whose operands are
+//      the stashed tiles read back as MN-major UMMA operands (same bytes, no transpose).
+//
+// Why the weight gradient is a second kernel: one layer's dW (256 x 256 fp32) fills all of TMEM,
+// so it cannot be accumulated on chip next to the per-tile chain; see DESIGN.md section 5.
+//
+// Reference semantics: autograd of src/model.py:36-53 (what loss.backward() does in
+// src/trainer.py:82 and src/optimizer.py:92).
+#include "sm100_common.cuh"
+
+using namespace sm100;
+
+namespace {
+
+constexpr int kBwdThreads = 384;   // warp 0 producer, 1 MMA, 2-5 group X, 6-9 group Y, 10/11 aux X/Y
+
+struct BwdStep {
+    uint32_t w_off;       // W^T stage images of the layer this step back-propagates through (step >= 1)
+    uint8_t n_kchunks;    // 64-wide K chunks of the incoming dY operand (2 or 4)
+    int8_t mask_layer;    // fwd layer whose ReLU mask gates the result (-1: none)
+    uint8_t add_sigma;    // result += dsigma_pre * w_sigma (gradient entering through the sigma head)
+    uint8_t out_layer;    // fwd layer whose pre-activation gradient (dY) this step produces
+    uint8_t out_blocks;   // 2 (128 wide) or 4 (256 wide)
+    uint16_t pad;
+};
+
+struct BwdParams {
+    int n_layers, n_steps;
+    FwdLayer layers[kMaxLayers];
+    BwdStep steps[kMaxLayers];
+    const uint8_t* packed;
+    const float* folded;
+    int n_folded, n_codes;
+    int64_t rows_per_code;
+    const float *w_sigma, *b_sigma, *w_rgb2;
+    int mode;                       // 0: rows are samples of rays (rs), 1: xyz / viewdir arrays
+    CnbRaySource rs;
+    const float *xyz, *viewdir;
+    int64_t S, row_offset;          // rows of this launch; global row of its first row (codes, rays)
+    const float *d_sigmas, *d_rgbs; // seeds, launch-relative rows: [S], [S,3]
+    uint32_t* mask_scratch;         // [grid][2][n_layers][8][128]
+    float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l
+    int stash;                      // 1: stream operand tiles + dspre to HBM (training)
+    uint8_t *stashA, *stashD;
+    float* dspre;                   // [S] d(loss)/d(sigma pre-activation)
+    uint32_t a_slot[kMaxLayers + 1];// byte offset in a tile's A stash of the input of layer l; [n_layers] = rgb.2 input
+    uint32_t dir_slot;
+    uint32_t d_slot[kMaxLayers];    // byte offset in a tile's dY stash of dY_l
+    uint32_t a_tile_bytes, d_tile_bytes;
+};
+
+__device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(umma::smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+__global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constant__ BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA0 = smem;
+    uint8_t* sW = smem + 2 * kATile;
+    uint64_t* bars = (uint64_t*)(sW + kNumStages * kSlot);
+    uint64_t* w_full = bars;
+    uint64_t* w_empty = bars + kNumStages;
+    uint64_t* a_ready = bars + 2 * kNumStages;   // [2] operand of the next MMA is in shared memory
+    uint64_t* acc_full = a_ready + 2;            // [2] accumulator complete
+    uint64_t* aux_ready = acc_full + 2;          // [2] a tile operand was (re)written (every phase)
+    uint64_t* buf_free = aux_ready + 2;          // [2] aux warp finished reading the operand buffer
+    uint32_t* tmem_slot = (uint32_t*)(buf_free + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nl = p.n_layers, ns = p.n_steps;
+    const int n_ops = nl + ns - 1;               // MMA operations per tile
+
+    const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
+    const int64_t tbase = tiles / gridDim.x, trem = tiles % gridDim.x;
+    const int64_t tile0 = (int64_t)blockIdx.x * tbase + min((int64_t)blockIdx.x, trem);
+    const int T = (int)(tbase + ((int64_t)blockIdx.x < trem ? 1 : 0));
+    const int rounds = (T + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], 1); }
+        for (int g = 0; g < 2; ++g) {
+            umma::mbar_init(&a_ready[g], 4); umma::mbar_init(&acc_full[g], 1);
+            umma::mbar_init(&aux_ready[g], 4); umma::mbar_init(&buf_free[g], 1);
+        }
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== weight producer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int r = 0; r < rounds; ++r)
+                for (int op = 0; op < n_ops; ++op)
+                    for (int g = 0; g < 2; ++g) {
+                        if (2 * r + g >= T) continue;
+                        uint32_t w_off; int n_main, n_dir;
+                        if (op < nl) {
+                            const FwdLayer& L = p.layers[op];
+                            w_off = L.w_off; n_main = L.n_kchunks * L.n_halves; n_dir = L.has_dir ? L.n_halves : 0;
+                        } else {
+                            const BwdStep& B = p.steps[op - nl + 1];
+                            w_off = B.w_off; n_main = B.n_kchunks * 2; n_dir = 0;
+                        }
+                        for (int s = 0; s < n_main + n_dir; ++s) {
+                            umma::mbar_wait(&w_empty[stage], ph ^ 1);
+                            const uint32_t bytes = s < n_main ? kSlot : kSlot / 2;
+                            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
+                            umma::bulk_g2s(sW + stage * kSlot, p.packed + w_off + (size_t)s * kSlot, bytes, &w_full[stage]);
+                            if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+                        }
+                    }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            const uint32_t idesc = umma::make_idesc(128, 128, 0, 0);
+            for (int r = 0; r < rounds; ++r)
+                for (int op = 0; op < n_ops; ++op)
+                    for (int g = 0; g < 2; ++g) {
+                        if (2 * r + g >= T) continue;
+                        int n_kchunks, n_halves, has_dir;
+                        if (op < nl) { n_kchunks = p.layers[op].n_kchunks; n_halves = p.layers[op].n_halves; has_dir = p.layers[op].has_dir; }
+                        else { n_kchunks = p.steps[op - nl + 1].n_kchunks; n_halves = 2; has_dir = 0; }
+                        umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u);
+                        umma::tc_fence_after();
+                        const uint32_t a_base = umma::smem_u32(sA0 + g * kATile);
+                        const uint32_t d_base = tmem + (uint32_t)g * 256u;
+                        for (int c = 0; c < n_kchunks; ++c)
+                            for (int h = 0; h < n_halves; ++h) {
+                                umma::mbar_wait(&w_full[stage], ph);
+                                umma::tc_fence_after();
+                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
+#pragma unroll
+                                for (int ks = 0; ks < 4; ++ks) {
+                                    const uint64_t da = umma::make_sdesc(a_base + c * kABlock + ks * 32, 16, 1024, umma::SWZ_128B);
+                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 1024, umma::SWZ_128B);
+                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, (c | ks) ? 1u : 0u);
+                                }
+                                umma::mma_commit(&w_empty[stage]);
+                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+                            }
+                        if (has_dir)
+                            for (int h = 0; h < n_halves; ++h) {
+                                umma::mbar_wait(&w_full[stage], ph);
+                                umma::tc_fence_after();
+                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
+#pragma unroll
+                                for (int ks = 0; ks < 2; ++ks) {
+                                    const uint64_t da = umma::make_sdesc(a_base + 4 * kABlock + ks * 32, 16, 512, umma::SWZ_64B);
+                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 512, umma::SWZ_64B);
+                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, 1u);
+                                }
+                                umma::mma_commit(&w_empty[stage]);
+                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+                            }
+                        umma::mma_commit(&acc_full[g]);
+                    }
+        }
+    } else if (warp >= 10) {
+        // ===== auxiliary warps: operand stash (TMA bulk stores) and column sums of every dY =====
+        const int g = warp - 10;
+        const uint8_t* sA = sA0 + g * kATile;
+        uint32_t ap = 0;
+        const int n_phases = nl + 1 + ns;
+        for (int r = 0; r < rounds; ++r) {
+            const int t = 2 * r + g;
+            if (t >= T) break;
+            const int64_t tile = tile0 + t;
+            int64_t code = 0;
+            if (p.n_codes > 1) { code = (p.row_offset + tile * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+            for (int phs = 0; phs < n_phases; ++phs) {
+                if (phs == nl && !p.stash) continue;      // the rgb.2 input is only written for the stash
+                umma::mbar_wait(&aux_ready[g], ap & 1u); ++ap;
+                int blocks = 0, out_layer = -1;
+                uint8_t* dst = nullptr;
+                if (phs == 0) { blocks = 1; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[0]; }
+                else if (phs < nl) { blocks = 4; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[phs]; }
+                else if (phs == nl) { blocks = 2; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[nl]; }
+                else {
+                    const BwdStep& B = p.steps[phs - nl - 1];
+                    blocks = B.out_blocks; out_layer = B.out_layer;
+                    dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
+                }
+                if (p.stash && lane == 0) {
+                    umma::bulk_s2g(dst, sA, (uint32_t)blocks * kABlock);
+                    if (phs == 0)
+                        umma::bulk_s2g(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock);
+                    umma::bulk_commit();
+                }
+                if (out_layer >= 0 && lane < blocks * 8) {
+                    const int blk = lane >> 3, chunk = lane & 7;
+                    float acc[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                    const uint8_t* base = sA + blk * kABlock;
+#pragma unroll 4
+                    for (int rr = 0; rr < kTileRows; ++rr) {
+                        const uint4 w = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                        acc[0] += bf_lo(w.x); acc[1] += bf_hi(w.x); acc[2] += bf_lo(w.y); acc[3] += bf_hi(w.y);
+                        acc[4] += bf_lo(w.z); acc[5] += bf_hi(w.z); acc[6] += bf_lo(w.w); acc[7] += bf_hi(w.w);
+                    }
+                    float* out = p.colsum + ((size_t)code * nl + out_layer) * kW + blk * 64 + chunk * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
+                }
+                if (p.stash && lane == 0) umma::bulk_wait_read_all();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&buf_free[g]);
+            }
+        }
+        if (p.stash && lane == 0) umma::bulk_wait_all();
+    } else {
+        // ===== compute groups =====
+        const int g = (warp - 2) >> 2;
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint8_t* sA = sA0 + g * kATile;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+        const int N = p.rs.N;
+        uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
+        uint32_t opc = 0;     // accumulator phases consumed
+        uint32_t* mscr = p.mask_scratch + ((size_t)(blockIdx.x * 2 + g) * nl) * 8 * kTileRows + row;
+
+        auto wait_buf_free = [&]() { if (wp > 0) umma::mbar_wait(&buf_free[g], (wp - 1) & 1u); };
+        auto publish = [&](bool to_mma) {
+            umma::tc_fence_before();
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) { if (to_mma) umma::mbar_arrive(&a_ready[g]); umma::mbar_arrive(&aux_ready[g]); }
+            ++wp;
+        };
+
+        for (int r = 0; r < rounds; ++r) {
+            const int t = 2 * r + g;
+            if (t >= T) break;
+            const int64_t lrow = (tile0 + t) * kTileRows + row;      // launch-relative row
+            const bool valid = lrow < p.S;
+            const int64_t grow = p.row_offset + lrow;                // global row
+            float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+            float ds = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
+            if (valid) {
+                if (p.mode == 0) {
+                    const int64_t ray = grow / N;
+                    const int zi = (int)(grow - ray * N);
+                    float o[3];
+                    cnb_fetch_ray(p.rs, ray, o, dir);
+                    const int64_t seg = ray / p.rs.rays_per_segment;
+                    const float z = __ldg(p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0) + zi);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + lrow * 3 + k); dir[k] = __ldg(p.viewdir + lrow * 3 + k); }
+                }
+                ds = __ldg(p.d_sigmas + lrow);
+                dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
+            }
+            int64_t code = 0;
+            if (p.n_codes > 1) { code = (p.row_offset + (tile0 + t) * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+
+            // ---- phase F0: positional encodings ----
+            wait_buf_free();
+            encode_row(pos, dir, valid, sA, sA + 4 * kABlock, row);
+            publish(true);
+
+            // ---- forward chain (recompute) ----
+            float sig_pre = 0.f;
+            for (int l = 0; l < nl; ++l) {
+                const FwdLayer& L = p.layers[l];
+                umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
+                umma::tc_fence_after();
+                const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
+                const int ncc = L.n_halves * 4;
+                const bool last = (l + 1 == nl);
+                const bool store = !last || p.stash;
+                if (store) wait_buf_free();
+                for (int cc = 0; cc < ncc; ++cc) {
+                    uint32_t rr[32];
+                    umma::tmem_ld32(taddr + cc * 32, rr);
+                    umma::tmem_ld_wait();
+                    uint32_t mw = 0u;
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const int col = cc * 32 + j8 * 8;
+                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+                        float v[8];
+                        v[0] = __uint_as_float(rr[j8 * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[j8 * 8 + 1]) + b0.y;
+                        v[2] = __uint_as_float(rr[j8 * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[j8 * 8 + 3]) + b0.w;
+                        v[4] = __uint_as_float(rr[j8 * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[j8 * 8 + 5]) + b1.y;
+                        v[6] = __uint_as_float(rr[j8 * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[j8 * 8 + 7]) + b1.w;
+                        if (L.relu) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                v[i] = fmaxf(v[i], 0.f);
+                                // mask bit (31 - column % 32): top bit of (bits + 0x7fffffff) is set iff v > 0
+                                mw = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, mw, 1);
+                            }
+                        }
+                        if (L.kind == 1) {
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col + 4));
+                            sig_pre = fmaf(v[0], w0.x, sig_pre); sig_pre = fmaf(v[1], w0.y, sig_pre);
+                            sig_pre = fmaf(v[2], w0.z, sig_pre); sig_pre = fmaf(v[3], w0.w, sig_pre);
+                            sig_pre = fmaf(v[4], w1.x, sig_pre); sig_pre = fmaf(v[5], w1.y, sig_pre);
+                            sig_pre = fmaf(v[6], w1.z, sig_pre); sig_pre = fmaf(v[7], w1.w, sig_pre);
+                        }
+                        if (store) {
+                            const int blk = cc >> 1, chunk = ((cc & 1) << 2) + j8;
+                            st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4),
+                                         umma::pack_bf16(v[0], v[1]), umma::pack_bf16(v[2], v[3]),
+                                         umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
+                        }
+                    }
+                    if (L.relu) mscr[((size_t)l * 8 + cc) * kTileRows] = mw;
+                }
+                if (store) publish(!last);
+            }
+            const float x = sig_pre + __ldg(p.b_sigma);
+            const float ex = expf(x);
+            const float dspre = x > 20.f ? ds : ds * ex / (ex + 1.f);      // softplus backward (ATen form)
+            if (p.stash && valid) p.dspre[lrow] = dspre;
+
+            // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
+            wait_buf_free();
+            uint32_t mlast = 0u;
+#pragma unroll
+            for (int c8 = 0; c8 < 16; ++c8) {
+                if ((c8 & 3) == 0) mlast = mscr[((size_t)(nl - 1) * 8 + (c8 >> 2)) * kTileRows];
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int col = c8 * 8 + i;
+                    float a = dcr * __ldg(p.w_rgb2 + col);
+                    a = fmaf(dcg, __ldg(p.w_rgb2 + (kW / 2) + col), a);
+                    a = fmaf(dcb, __ldg(p.w_rgb2 + kW + col), a);
+                    const uint32_t keep = (uint32_t)((int32_t)(mlast << (col & 31)) >> 31);
+                    v[i] = __uint_as_float(__float_as_uint(a) & keep);
+                }
+                const int blk = c8 >> 3, chunk = c8 & 7;
+                st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4), umma::pack_bf16(v[0], v[1]),
+                             umma::pack_bf16(v[2], v[3]), umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
+            }
+            publish(ns > 1);
+
+            // ---- input-gradient chain ----
+            for (int s = 1; s < ns; ++s) {
+                const BwdStep& B = p.steps[s];
+                umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
+                umma::tc_fence_after();
+                wait_buf_free();
+                const bool has_mask = B.mask_layer >= 0;
+                for (int cc = 0; cc < 8; ++cc) {
+                    uint32_t rr[32];
+                    umma::tmem_ld32(taddr + cc * 32, rr);
+                    const uint32_t mw = has_mask ? mscr[((size_t)B.mask_layer * 8 + cc) * kTileRows] : 0xffffffffu;
+                    umma::tmem_ld_wait();
+#pragma unroll
+                    for (int j8 = 0; j8 < 4; ++j8) {
+                        const int col = cc * 32 + j8 * 8;
+                        float v[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[j8 * 8 + i]);
+                        if (B.add_sigma) {
+                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col));
+                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col + 4));
+                            v[0] = fmaf(dspre, w0.x, v[0]); v[1] = fmaf(dspre, w0.y, v[1]);
+                            v[2] = fmaf(dspre, w0.z, v[2]); v[3] = fmaf(dspre, w0.w, v[3]);
+                            v[4] = fmaf(dspre, w1.x, v[4]); v[5] = fmaf(dspre, w1.y, v[5]);
+                            v[6] = fmaf(dspre, w1.z, v[6]); v[7] = fmaf(dspre, w1.w, v[7]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const uint32_t keep = (uint32_t)((int32_t)(mw << (j8 * 8 + i)) >> 31);
+                            v[i] = __uint_as_float(__float_as_uint(v[i]) & keep);
+                        }
+                        const int blk = cc >> 1, chunk = ((cc & 1) << 2) + j8;
+                        st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4),
+                                     umma::pack_bf16(v[0], v[1]), umma::pack_bf16(v[2], v[3]),
+                                     umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
+                    }
+                }
+                publish(s + 1 < ns);
+            }
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// ===========================================================================
+// K3: weight gradients from the stashed operand tiles.
+struct WgProblem {
+    uint32_t d_off;       // byte offset of dY_l inside a tile's dY stash
+    uint32_t a_off;       // byte offset of the layer input inside a tile's A stash
+    int64_t w_off;        // float offset of dW inside the flat parameter-gradient vector
+    int32_t ld;           // fan_in: row stride of dW
+    int32_t col0;         // first dW column this problem writes
+    int32_t n_valid;      // valid columns
+    uint8_t m_blocks;     // dY width / 64 (2 or 4)
+    uint8_t n_blocks;     // input width / 64 (1 or 4)
+    uint8_t is_dir;       // input is the [128 x 32] PE(viewdir) block (64-B swizzle)
+    uint8_t pad;
+    int32_t splits;       // work items this problem is cut into (along rows)
+    int32_t item0;        // index of its first work item
+};
+struct WgParams {
+    int n_problems, n_items;
+    WgProblem prob[kMaxLayers + 1];
+    const uint8_t *stashA, *stashD;
+    uint32_t a_tile_bytes, d_tile_bytes;
+    int64_t n_tiles;
+    float* dP;
+};
+constexpr int kWgStage = 65536;      // 64 rows: dY half-blocks [0, 32 KB) + input half-blocks [32 KB, 64 KB)
+constexpr int kWgStages = 3;
+constexpr int kWgThreads = 192;      // warp 0 producer, warp 1 MMA, warps 2-5 flush
+
+__device__ __forceinline__ void wg_item(const WgParams& p, int item, int& pi, int64_t& h_begin, int64_t& h_end) {
+    pi = 0;
+    while (pi + 1 < p.n_problems && item >= p.prob[pi + 1].item0) ++pi;
+    const int s = item - p.prob[pi].item0;
+    const int64_t H = p.n_tiles * 2;
+    const int64_t sp = p.prob[pi].splits;
+    h_begin = H * s / sp; h_end = H * (s + 1) / sp;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__ WgParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + kWgStages * kWgStage);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + kWgStages;
+    uint64_t* acc_done = bars + 2 * kWgStages;
+    uint64_t* acc_free = acc_done + 1;
+    uint32_t* tmem_slot = (uint32_t*)(acc_free + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWgStages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+        umma::mbar_init(acc_done, 1); umma::mbar_init(acc_free, 4);
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                int pi; int64_t hb, he;
+                wg_item(p, item, pi, hb, he);
+                const WgProblem& P = p.prob[pi];
+                const uint32_t bytes = P.m_blocks * 8192u + (P.is_dir ? 4096u : P.n_blocks * 8192u);
+                for (int64_t h = hb; h < he; ++h) {
+                    const int64_t tile = h >> 1; const uint32_t half = (uint32_t)(h & 1);
+                    umma::mbar_wait(&empty[stage], ph ^ 1);
+                    umma::mbar_arrive_expect_tx(&full[stage], bytes);
+                    uint8_t* dst = smem + stage * kWgStage;
+                    const uint8_t* srcD = p.stashD + (size_t)tile * p.d_tile_bytes + P.d_off + half * 8192u;
+                    for (int b = 0; b < P.m_blocks; ++b) umma::bulk_g2s(dst + b * 8192, srcD + (size_t)b * kABlock, 8192, &full[stage]);
+                    if (P.is_dir) {
+                        umma::bulk_g2s(dst + 32768, p.stashA + (size_t)tile * p.a_tile_bytes + P.a_off + half * 4096u, 4096, &full[stage]);
+                    } else {
+                        const uint8_t* srcA = p.stashA + (size_t)tile * p.a_tile_bytes + P.a_off + half * 8192u;
+                        for (int b = 0; b < P.n_blocks; ++b) umma::bulk_g2s(dst + 32768 + b * 8192, srcA + (size_t)b * kABlock, 8192, &full[stage]);
+                    }
+                    if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0; uint32_t it = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+                int pi; int64_t hb, he;
+                wg_item(p, item, pi, hb, he);
+                const WgProblem& P = p.prob[pi];
+                const uint32_t idesc = umma::make_idesc(128, P.is_dir ? 32 : P.n_blocks * 64, 1, 1);
+                if (it > 0) { umma::mbar_wait(acc_free, (it - 1) & 1u); umma::tc_fence_after(); }
+                for (int64_t h = hb; h < he; ++h) {
+                    umma::mbar_wait(&full[stage], ph);
+                    umma::tc_fence_after();
+                    const uint32_t sb = umma::smem_u32(smem + stage * kWgStage);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t db = P.is_dir ? umma::make_sdesc(sb + 32768 + ks * 1024, 4096, 512, umma::SWZ_64B)
+                                                     : umma::make_sdesc(sb + 32768 + ks * 2048, 8192, 1024, umma::SWZ_128B);
+                        for (int mh = 0; mh < P.m_blocks / 2; ++mh) {
+                            const uint64_t da = umma::make_sdesc(sb + mh * 16384 + ks * 2048, 8192, 1024, umma::SWZ_128B);
+                            umma::mma_bf16(tmem + mh * 256, da, db, idesc, (h > hb || ks > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma::mma_commit(&empty[stage]);
+                    if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+                }
+                umma::mma_commit(acc_done);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        uint32_t it = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            int pi; int64_t hb, he;
+            wg_item(p, item, pi, hb, he);
+            const WgProblem& P = p.prob[pi];
+            umma::mbar_wait(acc_done, it & 1u);
+            umma::tc_fence_after();
+            const int ncols = P.is_dir ? 32 : P.n_blocks * 64;
+            for (int mh = 0; mh < P.m_blocks / 2; ++mh) {
+                float* out = p.dP + P.w_off + (size_t)(mh * 128 + row) * P.ld + P.col0;
+                for (int cc = 0; cc < ncols; cc += 32) {
+                    uint32_t rr[32];
+                    umma::tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mh * 256 + cc, rr);
+                    umma::tmem_ld_wait();
+                    if (he > hb) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (cc + j < P.n_valid) atomicAdd(out + cc + j, __uint_as_float(rr[j]));
+                    }
+                }
+            }
+            umma::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(acc_free);
+        }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------
+// Narrow-head weight gradients from the stash: d(sigma.weight) = sum dspre * f, d(rgb.2.weight) = sum d_rgb (x) r1,
+// and their biases.  Thread t owns column t; rows are streamed tile by tile.
+__global__ void k_head_wgrad(const uint8_t* __restrict__ stashA, uint32_t a_tile_bytes, uint32_t f_off, uint32_t r1_off,
+                             const float* __restrict__ dspre, const float* __restrict__ d_rgbs, int64_t S,
+                             int64_t n_tiles, float* __restrict__ d_wsigma, float* __restrict__ d_bsigma,
+                             float* __restrict__ d_wrgb2, float* __restrict__ d_brgb2) {
+    const int t = threadIdx.x;                 // 256 threads
+    float as = 0.f, ar = 0.f, ag = 0.f, ab = 0.f, bs = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint8_t* base = stashA + (size_t)tile * a_tile_bytes;
+        const int rows = (int)min((int64_t)kTileRows, S - tile * kTileRows);
+        for (int r = 0; r < rows; ++r) {
+            const int64_t gr = tile * kTileRows + r;
+            const float dsp = __ldg(dspre + gr);
+            const uint16_t fv = *reinterpret_cast<const uint16_t*>(base + f_off + (t >> 6) * kABlock + umma::sw128_offset(r, t & 63));
+            as = fmaf(dsp, __uint_as_float((uint32_t)fv << 16), as);
+            if (t < 128) {
+                const uint16_t rv = *reinterpret_cast<const uint16_t*>(base + r1_off + (t >> 6) * kABlock + umma::sw128_offset(r, t & 63));
+                const float h = __uint_as_float((uint32_t)rv << 16);
+                ar = fmaf(__ldg(d_rgbs + gr * 3 + 0), h, ar);
+                ag = fmaf(__ldg(d_rgbs + gr * 3 + 1), h, ag);
+                ab = fmaf(__ldg(d_rgbs + gr * 3 + 2), h, ab);
+            }
+            if (t == 0) { bs += dsp; b0 += __ldg(d_rgbs + gr * 3); b1 += __ldg(d_rgbs + gr * 3 + 1); b2 += __ldg(d_rgbs + gr * 3 + 2); }
+        }
+    }
+    atomicAdd(d_wsigma + t, as);
+    if (t < 128) { atomicAdd(d_wrgb2 + t, ar); atomicAdd(d_wrgb2 + 128 + t, ag); atomicAdd(d_wrgb2 + 256 + t, ab); }
+    if (t == 0) { atomicAdd(d_bsigma, bs); atomicAdd(d_brgb2, b0); atomicAdd(d_brgb2 + 1, b1); atomicAdd(d_brgb2 + 2, b2); }
+}
+
+// Bias gradients: db_l[n] += sum_codes colsum[code][l][n].
+__global__ void k_bias_from_colsum(const float* __restrict__ colsum, int n_codes, int nl, int l, int n_out,
+                                   float* __restrict__ db) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= n_out) return;
+    float a = 0.f;
+    for (int c = 0; c < n_codes; ++c) a += colsum[((size_t)c * nl + l) * kW + n];
+    db[n] += a;
+}
+
+// Folded layers: dz[code][k] = sum_n cs[code][n] W[n][k]  (gradient reaching the latent branch output),
+// and the rank-1 weight term the fold moved out of the GEMM: dW[n][k] += cs[code][n] * z[code][k].
+__global__ void k_fold_bwd(const float* __restrict__ Wj, const float* __restrict__ cs /*[n_codes] stride cs_ld*/,
+                           int64_t cs_ld, const float* __restrict__ z, int64_t z_ld, float* __restrict__ dz,
+                           float* __restrict__ dW) {
+    const int code = blockIdx.x, k = threadIdx.x;      // 256 threads
+    const float* c = cs + (size_t)code * cs_ld;
+    const float zk = z[(size_t)code * z_ld + k];
+    float a = 0.f;
+    for (int n = 0; n < kW; ++n) {
+        const float cn = c[n];
+        a = fmaf(cn, __ldg(Wj + (size_t)n * kW + k), a);
+        if (dW && cn != 0.f) atomicAdd(dW + (size_t)n * kW + k, cn * zk);
+    }
+    dz[(size_t)code * z_ld + k] = a;
+}
+
+// d_rgb seed of the fused training step (mean L2 over each segment, src/trainer.py:75).
+__global__ void k_l2_seed_sm100(const float* __restrict__ rgb, const float* __restrict__ target, int64_t n_rays,
+                                int64_t ray0, int rays_per_segment, float scale, float* __restrict__ d_rgb,
+                                float* __restrict__ sq_err) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rays) return;
+    float e2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float e = rgb[(ray0 + r) * 3 + k] - target[(ray0 + r) * 3 + k];
+        d_rgb[r * 3 + k] = 2.f * e / (3.f * (float)rays_per_segment) * scale;
+        e2 += e * e;
+    }
+    if (sq_err) atomicAdd(sq_err + (ray0 + r) / rays_per_segment, e2);
+}
+
+// ===========================================================================
+// Host side
+
+constexpr int64_t kMaxSubTiles = 8192;     // rows per sub-batch = 1 Mi (stash ~ 8 GB)
+
+struct StashLayout {
+    uint32_t a_slot[kMaxLayers + 1], dir_slot, d_slot[kMaxLayers], a_tile_bytes, d_tile_bytes;
+};
+StashLayout make_stash_layout(const Plan& pl) {
+    StashLayout s = {};
+    uint32_t off = 0;
+    s.a_slot[0] = off; off += kABlock;                                   // PE(xyz)
+    for (int l = 1; l < pl.n_layers; ++l) { s.a_slot[l] = off; off += 4 * kABlock; }
+    s.a_slot[pl.n_layers] = off; off += 2 * kABlock;                     // rgb.2 input (128 wide)
+    s.dir_slot = off; off += kABlock;                                    // PE(viewdir), 8 KB used
+    s.a_tile_bytes = off;
+    off = 0;
+    for (int l = 0; l < pl.n_layers; ++l) { s.d_slot[l] = off; off += (uint32_t)pl.fwd[l].n_halves * 2 * kABlock; }
+    s.d_tile_bytes = off;
+    return s;
+}
+
+struct BwdWorkspace {
+    FwdWorkspace fw;
+    float *colsum, *dz;
+    uint32_t* masks;
+    float *spill_sig, *spill_rgb, *dsig, *drgb, *dspre, *ray_drgb, *ray_rgb, *ray_depth, *ray_acc;
+    uint8_t *stashA, *stashD;
+    size_t bytes;
+};
+
+size_t carve_bwd(const cnb_net_config* c, const Plan& pl, int n_codes, int64_t sub_rows, int64_t sub_rays, int fused,
+                 int stash, int grid, char* base, BwdWorkspace* out) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; };
+    BwdWorkspace w = {};
+    const int nf = c->shape_blocks + c->texture_blocks, nl = pl.n_layers;
+    w.fw.z = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    w.fw.folded = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    w.colsum = (float*)take(sizeof(float) * (size_t)n_codes * nl * kW);
+    w.dz = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    w.masks = (uint32_t*)take(sizeof(uint32_t) * (size_t)grid * 2 * nl * 8 * kTileRows);
+    w.dspre = (float*)take(sizeof(float) * (size_t)sub_rows);
+    if (fused) {
+        w.spill_sig = (float*)take(sizeof(float) * (size_t)sub_rows);
+        w.spill_rgb = (float*)take(sizeof(float) * (size_t)sub_rows * 3);
+        w.dsig = (float*)take(sizeof(float) * (size_t)sub_rows);
+        w.drgb = (float*)take(sizeof(float) * (size_t)sub_rows * 3);
+        w.ray_drgb = (float*)take(sizeof(float) * (size_t)sub_rays * 3);
+        w.ray_rgb = (float*)take(sizeof(float) * (size_t)sub_rays * 3);
+        w.ray_depth = (float*)take(sizeof(float) * (size_t)sub_rays);
+        w.ray_acc = (float*)take(sizeof(float) * (size_t)sub_rays);
+    }
+    if (stash) {
+        const StashLayout sl = make_stash_layout(pl);
+        const int64_t tiles = (sub_rows + kTileRows - 1) / kTileRows;
+        w.stashA = (uint8_t*)take((size_t)tiles * sl.a_tile_bytes);
+        w.stashD = (uint8_t*)take((size_t)tiles * sl.d_tile_bytes);
+    }
+    w.bytes = off;
+    if (out) *out = w;
+    return off;
+}
+
+int num_sms() {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+// K2 (+ K3 and head gradients when d_params != null) over launch-relative rows [0, S).
+int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* packed, const Plan& pl, BwdWorkspace& w,
+                int mode, const CnbRaySource* rs, const float* xyz, const float* viewdir, int64_t S, int64_t row_offset,
+                int n_codes, int64_t rows_per_code, const float* d_sigmas, const float* d_rgbs, float* d_params,
+                cudaStream_t st) {
+    CnbLayout L; cnb_make_layout(c, &L);
+    const StashLayout sl = make_stash_layout(pl);
+    BwdParams bp = {};
+    bp.n_layers = pl.n_layers;
+    for (int i = 0; i < pl.n_layers; ++i) bp.layers[i] = pl.fwd[i];
+    // step s >= 1 back-propagates through fwd layer nl - s and produces dY of layer nl - s - 1
+    const int nl = pl.n_layers;
+    bp.n_steps = nl;
+    bp.steps[0] = BwdStep{0, 0, (int8_t)(nl - 1), 0, (uint8_t)(nl - 1), 2, 0};
+    for (int s = 1; s < nl; ++s) {
+        const int lay = nl - s, out = lay - 1;
+        BwdStep b = {};
+        b.w_off = pl.bwd_w_off[lay];
+        b.n_kchunks = (uint8_t)(pl.fwd[lay].n_halves * 2);
+        b.mask_layer = pl.fwd[out].relu ? (int8_t)out : (int8_t)-1;
+        b.add_sigma = pl.fwd[out].kind == 1 ? 1 : 0;
+        b.out_layer = (uint8_t)out; b.out_blocks = 4;
+        bp.steps[s] = b;
+    }
+    bp.packed = (const uint8_t*)packed; bp.folded = w.fw.folded; bp.n_folded = pl.n_folded; bp.n_codes = n_codes;
+    bp.rows_per_code = rows_per_code;
+    bp.w_sigma = P[L.i_sigma]; bp.b_sigma = P[L.i_sigma + 1]; bp.w_rgb2 = P[L.i_rgb2];
+    bp.mode = mode; if (rs) bp.rs = *rs; else bp.rs.N = 1;
+    bp.xyz = xyz; bp.viewdir = viewdir; bp.S = S; bp.row_offset = row_offset;
+    bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
+    bp.mask_scratch = w.masks; bp.colsum = w.colsum;
+    bp.stash = d_params ? 1 : 0; bp.stashA = w.stashA; bp.stashD = w.stashD; bp.dspre = w.dspre;
+    for (int l = 0; l <= nl; ++l) bp.a_slot[l] = sl.a_slot[l];
+    for (int l = 0; l < nl; ++l) bp.d_slot[l] = sl.d_slot[l];
+    bp.dir_slot = sl.dir_slot; bp.a_tile_bytes = sl.a_tile_bytes; bp.d_tile_bytes = sl.d_tile_bytes;
+
+    const int sms = num_sms();
+    const int64_t tiles = (S + kTileRows - 1) / kTileRows;
+    const int64_t units = (tiles + 1) / 2;
+    const int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
+    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256;
+    CNB_CUDA_TRY(cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cnb_prof_begin(CNB_K_BWD, st);
+    k_mlp_bwd<<<grid, kBwdThreads, smem, st>>>(bp);
+    cnb_prof_end(CNB_K_BWD, st);
+    CNB_LAUNCH_CHECK();
+    if (!d_params) return CNB_OK;
+
+    // ---- K3: weight gradients ----
+    WgParams wp = {};
+    int np = 0;
+    auto add = [&](int lay, int64_t w_off, int ld, int col0, int n_valid, int n_blocks, uint32_t a_off, int is_dir) {
+        WgProblem q = {};
+        q.d_off = sl.d_slot[lay]; q.a_off = a_off; q.w_off = w_off; q.ld = ld; q.col0 = col0; q.n_valid = n_valid;
+        q.m_blocks = (uint8_t)(pl.fwd[lay].n_halves * 2); q.n_blocks = (uint8_t)n_blocks; q.is_dir = (uint8_t)is_dir;
+        wp.prob[np++] = q;
+    };
+    {
+        int l = 0;
+        add(l, L.enc_xyz_w, L.d_xyz, 0, L.d_xyz, 1, sl.a_slot[l], 0); ++l;
+        for (int j = 0; j < c->shape_blocks; ++j, ++l) add(l, L.s_w[j], kW, 0, kW, 4, sl.a_slot[l], 0);
+        add(l, L.enc_shape_w, kW, 0, kW, 4, sl.a_slot[l], 0); ++l;
+        add(l, L.enc_vd_w, kW + L.d_dir, 0, kW, 4, sl.a_slot[l], 0);
+        add(l, L.enc_vd_w, kW + L.d_dir, kW, L.d_dir, 0, sl.dir_slot, 1); ++l;
+        for (int j = 0; j < c->texture_blocks; ++j, ++l) add(l, L.t_w[j], kW, 0, kW, 4, sl.a_slot[l], 0);
+        add(l, L.rgb0_w, kW, 0, kW, 4, sl.a_slot[l], 0);
+    }
+    // split rows so that ~2 work items per SM exist, each spanning >= 8 half-tiles
+    double total_cost = 0;
+    for (int i = 0; i < np; ++i) total_cost += (double)wp.prob[i].m_blocks * (wp.prob[i].is_dir ? 1 : wp.prob[i].n_blocks);
+    const int64_t H = tiles * 2;
+    int items = 0;
+    for (int i = 0; i < np; ++i) {
+        const double cost = (double)wp.prob[i].m_blocks * (wp.prob[i].is_dir ? 1 : wp.prob[i].n_blocks);
+        int64_t sp = (int64_t)(2.0 * sms * cost / total_cost + 0.5);
+        if (sp > H / 8) sp = H / 8;
+        if (sp < 1) sp = 1;
+        wp.prob[i].splits = (int32_t)sp; wp.prob[i].item0 = items; items += (int)sp;
+    }
+    wp.n_problems = np; wp.n_items = items;
+    wp.stashA = w.stashA; wp.stashD = w.stashD; wp.a_tile_bytes = sl.a_tile_bytes; wp.d_tile_bytes = sl.d_tile_bytes;
+    wp.n_tiles = tiles; wp.dP = d_params;
+    const size_t wsmem = 1024 + (size_t)kWgStages * kWgStage + 256;
+    CNB_CUDA_TRY(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
+    const int wgrid = items < sms ? items : sms;
+    cnb_prof_begin(CNB_K_WGRAD, st);
+    k_wgrad<<<wgrid, kWgThreads, wsmem, st>>>(wp);
+    cnb_prof_end(CNB_K_WGRAD, st);
+    CNB_LAUNCH_CHECK();
+    // narrow heads (sigma, rgb.2): inputs f (input of encoding_viewdir) and the rgb.0 hidden
+    int l_vd = 1 + c->shape_blocks + 1;
+    const int hgrid = (int)(tiles < 4 * sms ? tiles : 4 * sms);
+    k_head_wgrad<<<hgrid, 256, 0, st>>>(w.stashA, sl.a_tile_bytes, sl.a_slot[l_vd], sl.a_slot[nl], w.dspre, d_rgbs, S, tiles,
+                                       d_params + L.sigma_w, d_params + L.sigma_b, d_params + L.rgb2_w,
+                                       d_params + L.rgb2_b);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+}
+
+// After all rows: bias gradients, the per-code folded-layer terms and the latent branches.
+int finish_bwd(const cnb_net_config* c, const float* const* P, const Plan& pl, BwdWorkspace& w,
+               const float* shape_codes, const float* tex_codes, int n_codes, float* d_params, float* d_shape,
+               float* d_tex, cudaStream_t st) {
+    CnbLayout L; cnb_make_layout(c, &L);
+    const int nl = pl.n_layers, nf = pl.n_folded;
+    if (d_params) {
+        int64_t boff[kMaxLayers]; int l = 0;
+        boff[l++] = L.enc_xyz_b;
+        for (int j = 0; j < c->shape_blocks; ++j) boff[l++] = L.s_b[j];
+        boff[l++] = L.enc_shape_b; boff[l++] = L.enc_vd_b;
+        for (int j = 0; j < c->texture_blocks; ++j) boff[l++] = L.t_b[j];
+        boff[l++] = L.rgb0_b;
+        for (int i = 0; i < nl; ++i) {
+            const int n_out = pl.fwd[i].n_halves * 128;
+            k_bias_from_colsum<<<(n_out + 127) / 128, 128, 0, st>>>(w.colsum, n_codes, nl, i, n_out, d_params + boff[i]);
+            CNB_LAUNCH_CHECK();
+        }
+    }
+    CNB_CUDA_TRY(cudaMemsetAsync(d_shape, 0, sizeof(float) * (size_t)n_codes * c->latent_dim, st));
+    CNB_CUDA_TRY(cudaMemsetAsync(d_tex, 0, sizeof(float) * (size_t)n_codes * c->latent_dim, st));
+    const int64_t zld = (int64_t)nf * kW;
+    for (int l = 0; l < nl; ++l) {
+        const int j = pl.fwd[l].folded;
+        if (j < 0) continue;
+        const bool shape = j < c->shape_blocks;
+        const int jj = shape ? j : j - c->shape_blocks;
+        const int iw = shape ? L.i_s[jj] : L.i_t[jj];
+        const int il = shape ? L.i_sl[jj] : L.i_tl[jj];
+        const int64_t w_off = shape ? L.s_w[jj] : L.t_w[jj];
+        const int64_t lw_off = shape ? L.sl_w[jj] : L.tl_w[jj];
+        const int64_t lb_off = shape ? L.sl_b[jj] : L.tl_b[jj];
+        k_fold_bwd<<<n_codes, kW, 0, st>>>(P[iw], w.colsum + (size_t)l * kW, (int64_t)nl * kW, w.fw.z + (size_t)j * kW, zld,
+                                          w.dz + (size_t)j * kW, d_params ? d_params + w_off : nullptr);
+        CNB_LAUNCH_CHECK();
+        CNB_TRY(cnb_launch_latent_bwd(P[il], shape ? shape_codes : tex_codes, w.fw.z + (size_t)j * kW, w.dz + (size_t)j * kW,
+                                      zld, n_codes, c->latent_dim, kW, d_params ? d_params + lw_off : nullptr,
+                                      d_params ? d_params + lb_off : nullptr, shape ? d_shape : d_tex, st));
+    }
+    return CNB_OK;
+}
+
+}  // namespace
+
+// ===========================================================================
+namespace sm100 {
+
+size_t bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int64_t n_rays, int N, int n_codes, int fused) {
+    Plan pl;
+    if (make_plan(cfg, nullptr, &pl) != CNB_OK) return 256;
+    int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
+    int64_t sub_rays = fused ? (sub_rows / N < 1 ? 1 : sub_rows / N) : 0;
+    if (fused) { if (sub_rays > n_rays) sub_rays = n_rays; sub_rows = sub_rays * N; }
+    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, 148 * 2, nullptr, nullptr) + 1024;
+}
+
+// Fused render backward (mode 1: seeds given; mode 2: L2 loss against target).
+int render_backward(const cnb_net_config* cfg, const float* const* P, const void* packed, const cnb_ray_batch* rays,
+                    int mode, const float* d_rgb, const float* d_depth, const float* target, float loss_scale,
+                    float* rgb, float* depth, float* acc, float* sq_err, float* d_params, float* d_shape, float* d_tex,
+                    void* ws, size_t ws_bytes, cudaStream_t st) {
+    Plan pl;
+    CNB_TRY(make_plan(cfg, P, &pl));
+    const int N = rays->n_samples;
+    if (N > 512) return CNB_E_UNSUPPORTED;
+    const int64_t S = rays->n_rays * N;
+    const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * N;
+    if (rays->n_codes > 1 && (rows_per_code % kTileRows) != 0) return CNB_E_UNSUPPORTED;
+    int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
+    int64_t sub_rays = sub_rows / N < 1 ? 1 : sub_rows / N;
+    if (sub_rays > rays->n_rays) sub_rays = rays->n_rays;
+    if (rays->n_codes > 1) {   // sub-batches must start on tile-aligned rows so a tile never straddles codes
+        const int64_t align = kTileRows / (N % kTileRows == 0 ? kTileRows : 1);
+        (void)align;
+        while (sub_rays > 1 && (sub_rays * N) % kTileRows != 0) --sub_rays;
+        if ((sub_rays * N) % kTileRows != 0 && sub_rays < rays->n_rays) return CNB_E_UNSUPPORTED;
+    }
+    sub_rows = sub_rays * N;
+    BwdWorkspace w;
+    const size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr);
+    if (!ws || ws_bytes < need) return CNB_E_WORKSPACE;
+    if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
+    carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, (char*)ws, &w);
+    CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w.fw, st));
+    CNB_CUDA_TRY(cudaMemsetAsync(w.colsum, 0, sizeof(float) * (size_t)rays->n_codes * pl.n_layers * kW, st));
+    if (mode == 2 && sq_err)
+        CNB_CUDA_TRY(cudaMemsetAsync(sq_err, 0, sizeof(float) * (size_t)(rays->n_rays / rays->rays_per_segment), st));
+    CnbRaySource rs = cnb_make_ray_source(rays);
+    for (int64_t r0 = 0; r0 < rays->n_rays; r0 += sub_rays) {
+        const int64_t nr = rays->n_rays - r0 < sub_rays ? rays->n_rays - r0 : sub_rays;
+        // forward (spilling per-sample sigma / rgb for the compositing backward)
+        float* o_rgb = rgb ? rgb : w.ray_rgb - r0 * 3;
+        float* o_depth = depth ? depth : w.ray_depth - r0;
+        float* o_acc = acc ? acc : w.ray_acc - r0;
+        CNB_TRY(launch_render_rays(cfg, P, packed, pl, rays, r0, nr, w.fw.folded, w.spill_sig, w.spill_rgb, o_rgb, o_depth,
+                                   o_acc, st));
+        const float* seed_rgb; const float* seed_depth = nullptr;
+        if (mode == 2) {
+            k_l2_seed_sm100<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(o_rgb, target, nr, r0, rays->rays_per_segment,
+                                                                         loss_scale, w.ray_drgb, sq_err);
+            CNB_LAUNCH_CHECK();
+            seed_rgb = w.ray_drgb;
+        } else {
+            seed_rgb = d_rgb + r0 * 3;
+            seed_depth = d_depth ? d_depth + r0 : nullptr;
+        }
+        CNB_TRY(cnb_vr_backward_segments(w.spill_sig, w.spill_rgb, rays->z_vals, rays->z_per_segment,
+                                         rays->rays_per_segment, r0, nr, N, rays->white_bg, seed_rgb, seed_depth, w.dsig,
+                                         w.drgb, st));
+        CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 0, &rs, nullptr, nullptr, nr * N, r0 * N, rays->n_codes,
+                            rays->n_codes > 1 ? rows_per_code : S, w.dsig, w.drgb, d_params, st));
+    }
+    return finish_bwd(cfg, P, pl, w, rays->shape_codes, rays->texture_codes, rays->n_codes, d_params, d_shape, d_tex, st);
+}
+
+}  // namespace sm100
+
+int cnb_sm100_mlp_backward(const cnb_net_config* cfg, const float* const* P, const void* packed, const float* xyz,
+                           const float* viewdir, const float* shape_codes, const float* tex_codes, int n_codes,
+                           int64_t samples_per_code, int64_t S, const float* d_sigmas, const float* d_rgbs,
+                           float* d_params, float* d_shape, float* d_tex, void* ws, size_t ws_bytes, cudaStream_t st) {
+    Plan pl;
+    CNB_TRY(make_plan(cfg, P, &pl));
+    if (n_codes > 1 && (samples_per_code % kTileRows) != 0) return CNB_E_UNSUPPORTED;
+    const int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
+    BwdWorkspace w;
+    const size_t need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr);
+    if (!ws || ws_bytes < need) return CNB_E_WORKSPACE;
+    if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
+    carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, (char*)ws, &w);
+    CNB_TRY(latent_and_fold(cfg, P, shape_codes, tex_codes, n_codes, w.fw, st));
+    CNB_CUDA_TRY(cudaMemsetAsync(w.colsum, 0, sizeof(float) * (size_t)n_codes * pl.n_layers * kW, st));
+    for (int64_t r0 = 0; r0 < S; r0 += sub_rows) {
+        const int64_t m = S - r0 < sub_rows ? S - r0 : sub_rows;
+        CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 1, nullptr, xyz + r0 * 3, viewdir + r0 * 3, m, r0, n_codes,
+                            n_codes > 1 ? samples_per_code : S, d_sigmas + r0, d_rgbs + r0 * 3, d_params, st));
+    }
+    return finish_bwd(cfg, P, pl, w, shape_codes, tex_codes, n_codes, d_params, d_shape, d_tex, st);
+}
+
+size_t cnb_sm100_mlp_bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int n_codes) {
+    return sm100::bwd_workspace_bytes(cfg, S, 0, 1, n_codes, 0);
+}
+
+int cnb_sm100_has_backward(void) { return 1; }
+
+int cnb_sm100_pipeline_timeouts_bwd(void) {
+    unsigned int v = 0;
+    if (cudaMemcpyFromSymbol(&v, umma::g_umma_timeout, sizeof(unsigned int)) != cudaSuccess) return -1;
+    return (int)v;
+}

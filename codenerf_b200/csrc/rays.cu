@@ -132,7 +132,8 @@ __global__ void k_volume_rendering_fwd(const float* __restrict__ sigmas, const f
 // aT is an affine recurrence run backwards; each lane composes its run into
 // (A, Bc) with aT_in = A * aT_out + Bc, a warp suffix-scan composes the lanes.
 __global__ void k_volume_rendering_bwd(const float* __restrict__ sigmas, const float* __restrict__ rgbs,
-                                       const float* __restrict__ z, int64_t B, int N, int white_bg,
+                                       const float* __restrict__ z_base, int z_per_segment, int rays_per_segment,
+                                       int64_t ray_first, int64_t B, int N, int white_bg,
                                        const float* __restrict__ d_rgb, const float* __restrict__ d_depth,
                                        float* __restrict__ d_sigmas, float* __restrict__ d_rgbs) {
     const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -140,6 +141,7 @@ __global__ void k_volume_rendering_bwd(const float* __restrict__ sigmas, const f
     const int lane = threadIdx.x & 31;
     const int per = (N + 31) / 32;
     const int i0 = lane * per;
+    const float* z = z_base + (z_per_segment ? ((ray_first + ray) / rays_per_segment) * N : 0);
     const float gr = d_rgb[ray * 3], gg = d_rgb[ray * 3 + 1], gb = d_rgb[ray * 3 + 2];
     const float gd = d_depth ? d_depth[ray] : 0.f;
     const float bg = white_bg ? 1.f : 0.f;
@@ -227,8 +229,22 @@ extern "C" int cnb_volume_rendering_backward(const float* sigmas, const float* r
     if (B == 0) return CNB_OK;
     const int64_t blocks = (B * 32 + 255) / 256;
     if (blocks > 0x7fffffff) return CNB_E_UNSUPPORTED;
-    k_volume_rendering_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, z_vals, B, N, white_bg,
-                                                                               d_rgb, d_depth, d_sigmas, d_rgbs);
+    k_volume_rendering_bwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(sigmas, rgbs, z_vals, 0, 1, 0, B, N,
+                                                                               white_bg, d_rgb, d_depth, d_sigmas,
+                                                                               d_rgbs);
+    CNB_LAUNCH_CHECK();
+    return CNB_OK;
+}
+
+// Same kernel for a slice [ray0, ray0 + n_rays) of a segmented batch (one z row per segment).
+int cnb_vr_backward_segments(const float* sigmas, const float* rgbs, const float* z_vals, int z_per_segment,
+                             int rays_per_segment, int64_t ray0, int64_t n_rays, int N, int white_bg,
+                             const float* d_rgb, const float* d_depth, float* d_sigmas, float* d_rgbs, cudaStream_t st) {
+    if (N > 32 * VR_MAX_PER_LANE) return CNB_E_UNSUPPORTED;
+    if (n_rays <= 0) return CNB_OK;
+    const int64_t blocks = (n_rays * 32 + 255) / 256;
+    k_volume_rendering_bwd<<<(unsigned)blocks, 256, 0, st>>>(sigmas, rgbs, z_vals, z_per_segment, rays_per_segment, ray0,
+                                                            n_rays, N, white_bg, d_rgb, d_depth, d_sigmas, d_rgbs);
     CNB_LAUNCH_CHECK();
     return CNB_OK;
 }

@@ -10,34 +10,11 @@
 //
 // Reference semantics: src/model.py:36-53 (network), src/utils.py:10-47 (rays, sampling,
 // compositing).  See DESIGN.md for the tile / pipeline design and the roofline arithmetic.
-#include "render_sm100.cuh"
-#include "mlp_fp32.cuh"
-#include "umma.cuh"
+#include "sm100_common.cuh"
+
+using namespace sm100;
 
 namespace {
-
-constexpr int kW = 256;                 // layer width the tensor-core path implements
-constexpr int kLx = 10, kLd = 4;        // PE frequencies (63 / 27 channels)
-constexpr int kTileRows = 128;          // UMMA M
-constexpr int kSlot = 16384;            // one weight stage: [128 n x 64 k] bf16, 128-B swizzle
-constexpr int kNumStages = 4;
-constexpr int kABlock = 16384;          // activation K-block [128 rows x 64] bf16, 128-B swizzle
-constexpr int kDirBlock = 8192;         // PE(viewdir) block [128 rows x 32] bf16, 64-B swizzle
-constexpr int kATile = 4 * kABlock + kDirBlock;
-constexpr int kThreads = 320;           // warp 0 producer, warp 1 MMA, warps 2-5 group X, 6-9 group Y
-constexpr int kMaxLayers = 2 * CNB_MAX_BLOCKS + 4;
-
-struct FwdLayer {
-    uint32_t w_off;       // byte offset of the first stage slot inside the packed buffer
-    uint8_t n_kchunks;    // 64-wide K chunks taken from activation blocks 0..n-1
-    uint8_t has_dir;      // one more K=32 chunk from the PE(viewdir) block
-    uint8_t n_halves;     // n_out / 128
-    uint8_t relu;
-    uint8_t kind;         // 0 hidden, 1 encoding_shape (+ sigma head), 2 rgb.0 (+ rgb head)
-    int8_t folded;        // >= 0: bias row of the per-code folded table; < 0: shared bias
-    uint16_t pad;
-    const float* bias;    // shared bias [n_out] (fp32 parameter tensor)
-};
 
 struct FwdParams {
     int n_layers;
@@ -50,73 +27,13 @@ struct FwdParams {
     int mode;                     // 0: rays -> composite; 1: xyz / viewdir arrays -> sigmas, rgbs
     CnbRaySource rs;
     const float *xyz, *viewdir;
-    int64_t n_rays, S;
+    int64_t n_rays, S;            // rays / rows of THIS launch
+    int64_t ray_offset;           // mode 0: global index of this launch's first ray (sub-batching)
     int white_bg, ring_cap;
     float *rgb, *depth, *acc;
-    float4* samples_out;          // optional per-sample (sigma, r, g, b) spill for the training backward
+    float *spill_sig, *spill_rgb; // optional per-sample spill (launch-relative rows) for the training backward
     float *sigmas, *rgbs;
 };
-
-__device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(umma::smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
-                 : "memory");
-}
-
-// PE of one row into the operand blocks -- reference src/model.py:4-7 (x, sines, cosines).
-// sin/cos(2^i x) by exact doubling from an accurate sincosf(x): error < 2^i * 1e-7, far below bf16.
-__device__ __forceinline__ void encode_row(const float p[3], const float v[3], bool valid, uint8_t* blk0,
-                                           uint8_t* dirblk, int row) {
-    float e[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) e[i] = 0.f;
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            e[k] = p[k];
-            float s, c;
-            sincosf(p[k], &s, &c);
-#pragma unroll
-            for (int i = 0; i < kLx; ++i) {
-                e[3 + 3 * i + k] = s;
-                e[3 + 3 * kLx + 3 * i + k] = c;
-                const float s2 = 2.f * s * c;
-                c = fmaf(-2.f * s, s, 1.f);
-                s = s2;
-            }
-        }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        st_shared_v4(blk0 + row * 128 + ((ch ^ (row & 7)) << 4), umma::pack_bf16(e[ch * 8 + 0], e[ch * 8 + 1]),
-                     umma::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]), umma::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]),
-                     umma::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
-    }
-    float d[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) d[i] = 0.f;
-    if (valid) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            d[k] = v[k];
-            float s, c;
-            sincosf(v[k], &s, &c);
-#pragma unroll
-            for (int i = 0; i < kLd; ++i) {
-                d[3 + 3 * i + k] = s;
-                d[3 + 3 * kLd + 3 * i + k] = c;
-                const float s2 = 2.f * s * c;
-                c = fmaf(-2.f * s, s, 1.f);
-                s = s2;
-            }
-        }
-    }
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        st_shared_v4(dirblk + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4), umma::pack_bf16(d[ch * 8 + 0], d[ch * 8 + 1]),
-                     umma::pack_bf16(d[ch * 8 + 2], d[ch * 8 + 3]), umma::pack_bf16(d[ch * 8 + 4], d[ch * 8 + 5]),
-                     umma::pack_bf16(d[ch * 8 + 6], d[ch * 8 + 7]));
-    }
-}
 
 __device__ __forceinline__ float warp_excl_prod_f(float local, int lane) {
     float incl = local;
@@ -305,8 +222,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
             if (valid) {
                 if (p.mode == 0) {
-                    const int64_t ray = grow / N;
-                    const int zi = (int)(grow - ray * N);
+                    const int64_t lray = grow / N;
+                    const int zi = (int)(grow - lray * N);
+                    const int64_t ray = p.ray_offset + lray;
                     float o[3];
                     cnb_fetch_ray(p.rs, ray, o, dir);
                     const int64_t seg = ray / p.rs.rays_per_segment;
@@ -319,7 +237,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 }
             }
             int64_t code = 0;
-            if (p.n_codes > 1) { code = (valid ? grow : row0) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+            if (p.n_codes > 1) {
+                code = (p.ray_offset * N + (valid ? grow : row0)) / p.rows_per_code;
+                if (code >= p.n_codes) code = p.n_codes - 1;
+            }
             encode_row(pos, dir, valid, sA, sA + 4 * kABlock, row);
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
@@ -395,7 +316,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             const float4 smp = make_float4(sigma, cr, cg, cb);
             if (valid) {
                 sRing[lrow % p.ring_cap] = smp;
-                if (p.samples_out) p.samples_out[grow] = smp;
+                if (p.spill_sig) {
+                    p.spill_sig[grow] = sigma;
+                    p.spill_rgb[grow * 3 + 0] = cr; p.spill_rgb[grow * 3 + 1] = cg; p.spill_rgb[grow * 3 + 2] = cb;
+                }
             }
             umma::named_bar_sync(1 + g, 128);
             if (row == 0) { __threadfence_block(); final_count[g] = r + 1; }
@@ -411,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             const int64_t q_first = tile_lo / N;        // first ray whose last row lies in this tile
             const int64_t q_last = tile_hi / N - 1;     // last ray completed by the end of this tile
             for (int64_t qr = q_first + wi; qr <= q_last; qr += 4)
-                composite_ray(p, sRing, p.ring_cap, qr * N, ray0 + qr, lane);
+                composite_ray(p, sRing, p.ring_cap, qr * N, p.ray_offset + ray0 + qr, lane);
         }
     }
     umma::tc_fence_before();
@@ -490,49 +414,9 @@ __global__ void k_fold_bias(const float* __restrict__ Wj, const float* __restric
 }
 
 // ---------------------------------------------------------------------------
-struct Plan {
-    int n_layers, n_folded;
-    FwdLayer fwd[kMaxLayers];
-    size_t fwd_bytes, total_bytes;
-};
+}  // namespace
 
-int make_plan(const cnb_net_config* c, const float* const* P, Plan* pl) {
-    if (c->W != kW || c->num_xyz_freq != kLx || c->num_dir_freq != kLd) return CNB_E_UNSUPPORTED;
-    CnbLayout L; cnb_make_layout(c, &L);
-    int n = 0, nf = 0; size_t off = 0;
-    auto add = [&](int wi, int kch, int dir, int halves, int relu, int kind, int folded) {
-        FwdLayer f = {};
-        f.w_off = (uint32_t)off; f.n_kchunks = (uint8_t)kch; f.has_dir = (uint8_t)dir; f.n_halves = (uint8_t)halves;
-        f.relu = (uint8_t)relu; f.kind = (uint8_t)kind; f.folded = (int8_t)folded;
-        f.bias = P ? P[wi + 1] : nullptr;
-        off += (size_t)(kch + dir) * halves * kSlot;
-        pl->fwd[n++] = f;
-    };
-    add(L.i_enc_xyz, 1, 0, 2, 1, 0, -1);
-    for (int j = 0; j < c->shape_blocks; ++j) add(L.i_s[j], 4, 0, 2, 1, 0, nf++);
-    add(L.i_enc_shape, 4, 0, 2, 0, 1, -1);
-    add(L.i_enc_vd, 4, 1, 2, 1, 0, -1);
-    for (int j = 0; j < c->texture_blocks; ++j) add(L.i_t[j], 4, 0, 2, 1, 0, nf++);
-    add(L.i_rgb0, 4, 0, 1, 1, 2, -1);
-    pl->n_layers = n; pl->n_folded = nf; pl->fwd_bytes = off; pl->total_bytes = off;
-    return CNB_OK;
-}
-
-struct FwdWorkspace { float *z, *folded; float4* samples; size_t bytes; };
-
-size_t carve_fwd(const cnb_net_config* c, int n_codes, int64_t spill_samples, char* base, FwdWorkspace* w) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += (bytes + 255) & ~(size_t)255; return p; };
-    const int nf = c->shape_blocks + c->texture_blocks;
-    FwdWorkspace x = {};
-    x.z = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
-    x.folded = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
-    x.samples = (float4*)take(sizeof(float4) * (size_t)spill_samples);
-    x.bytes = off;
-    if (w) *w = x;
-    return off;
-}
-
+namespace sm100 {
 // z_j = ReLU(latent layer_j(code)) and the folded per-code biases.
 int latent_and_fold(const cnb_net_config* c, const float* const* P, const float* shape_codes, const float* tex_codes,
                     int n_codes, FwdWorkspace& w, cudaStream_t st) {
@@ -553,6 +437,11 @@ int latent_and_fold(const cnb_net_config* c, const float* const* P, const float*
     }
     return CNB_OK;
 }
+
+
+}  // namespace sm100
+
+namespace {
 
 int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packed, const Plan& pl, FwdParams& fp,
                int64_t total_rows, cudaStream_t st) {
@@ -615,17 +504,48 @@ int cnb_sm100_pack_weights(const cnb_net_config* cfg, const float* const* P, voi
     CNB_TRY(pack(L.i_enc_vd, kW + L.d_dir, kW, kW, kW, L.d_dir));
     for (int j = 0; j < cfg->texture_blocks; ++j) CNB_TRY(pack(L.i_t[j], kW, kW, kW, 0, 0));
     CNB_TRY(pack(L.i_rgb0, kW, kW / 2, kW, 0, 0));
+    // dgrad operands: B[n = k_in][k = n_out] = W[k][n], K chunks over n_out, two N halves over the first 256 inputs
+    for (int l = 1; l < pl.n_layers; ++l) {
+        const FwdLayer& f = pl.fwd[l];
+        PackArgs a = {};
+        a.W = P[pl.w_index[l]];
+        a.ld = f.has_dir ? kW + L.d_dir : kW;
+        a.n_total = kW; a.k_total = f.n_halves * 128; a.transpose = 1;
+        a.n_kchunks = f.n_halves * 2; a.n_halves = 2; a.has_dir = 0;
+        a.dst = (uint8_t*)packed + pl.bwd_w_off[l];
+        k_pack_layer<<<a.n_kchunks * 2, 256, 0, st>>>(a);
+        CNB_LAUNCH_CHECK();
+    }
     return CNB_OK;
 }
 
 size_t cnb_sm100_mlp_workspace_bytes(const cnb_net_config* cfg, int64_t S, int n_codes, int backward) {
-    (void)S; (void)backward;
+    if (backward) return bwd_workspace_bytes(cfg, S, 0, 1, n_codes, 0);
     return carve_fwd(cfg, n_codes, 0, nullptr, nullptr) + 256;
 }
 
 size_t cnb_sm100_render_workspace_bytes(const cnb_net_config* cfg, const cnb_ray_batch* rays, int backward) {
-    return carve_fwd(cfg, rays->n_codes, backward ? rays->n_rays * rays->n_samples : 0, nullptr, nullptr) + 256;
+    if (backward) return bwd_workspace_bytes(cfg, rays->n_rays * rays->n_samples, rays->n_rays, rays->n_samples, rays->n_codes, 1);
+    return carve_fwd(cfg, rays->n_codes, 0, nullptr, nullptr) + 256;
 }
+
+namespace sm100 {
+// K1 over rays [ray_begin, ray_begin + ray_count) of the batch; outputs indexed by global ray,
+// the optional per-sample spill by launch-relative row.
+int launch_render_rays(const cnb_net_config* cfg, const float* const* P, const void* packed, const Plan& pl,
+                       const cnb_ray_batch* rays, int64_t ray_begin, int64_t ray_count, const float* folded,
+                       float* spill_sig, float* spill_rgb, float* rgb, float* depth, float* acc, cudaStream_t st) {
+    const int N = rays->n_samples;
+    const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * N;
+    FwdParams fp = {};
+    fp.mode = 0; fp.rs = cnb_make_ray_source(rays); fp.n_rays = ray_count; fp.S = ray_count * N; fp.ray_offset = ray_begin;
+    fp.folded = folded; fp.n_codes = rays->n_codes;
+    fp.rows_per_code = rays->n_codes > 1 ? rows_per_code : rays->n_rays * N;
+    fp.white_bg = rays->white_bg;
+    fp.rgb = rgb; fp.depth = depth; fp.acc = acc; fp.spill_sig = spill_sig; fp.spill_rgb = spill_rgb;
+    return launch_fwd(cfg, P, packed, pl, fp, fp.S, st);
+}
+}  // namespace sm100
 
 int cnb_sm100_mlp_forward(const cnb_net_config* cfg, const float* const* P, const void* packed, const float* xyz,
                           const float* viewdir, const float* shape_codes, const float* tex_codes, int n_codes,
@@ -647,20 +567,15 @@ int cnb_sm100_mlp_forward(const cnb_net_config* cfg, const float* const* P, cons
     return launch_fwd(cfg, P, packed, pl, fp, S, st);
 }
 
-int cnb_sm100_mlp_backward(const cnb_net_config*, const float* const*, const void*, const float*, const float*,
-                           const float*, const float*, int, int64_t, int64_t, const float*, const float*, float*,
-                           float*, float*, void*, size_t, cudaStream_t) {
-    return CNB_E_UNSUPPORTED;
-}
-
 int cnb_sm100_render(const cnb_net_config* cfg, const float* const* P, const void* packed, const cnb_ray_batch* rays,
                      int mode, const float* d_rgb, const float* d_depth, const float* target, float loss_scale,
                      float* rgb, float* depth, float* acc, float* sq_err, float* d_params, float* d_shape,
                      float* d_tex, void* ws, size_t ws_bytes, cudaStream_t st) {
-    (void)d_rgb; (void)d_depth; (void)target; (void)loss_scale; (void)sq_err; (void)d_params; (void)d_shape; (void)d_tex;
+    if (mode != 0)
+        return render_backward(cfg, P, packed, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc, sq_err,
+                               d_params, d_shape, d_tex, ws, ws_bytes, st);
     Plan pl;
     CNB_TRY(make_plan(cfg, P, &pl));
-    if (mode != 0) return CNB_E_UNSUPPORTED;
     const int N = rays->n_samples;
     if (N > 512) return CNB_E_UNSUPPORTED;
     const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * N;
@@ -670,18 +585,12 @@ int cnb_sm100_render(const cnb_net_config* cfg, const float* const* P, const voi
     if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
     carve_fwd(cfg, rays->n_codes, 0, (char*)ws, &w);
     CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w, st));
-    FwdParams fp = {};
-    fp.mode = 0; fp.rs = cnb_make_ray_source(rays); fp.n_rays = rays->n_rays; fp.S = rays->n_rays * N;
-    fp.folded = w.folded; fp.n_codes = rays->n_codes; fp.rows_per_code = rays->n_codes > 1 ? rows_per_code : fp.S;
-    fp.white_bg = rays->white_bg;
-    fp.rgb = rgb; fp.depth = depth; fp.acc = acc;
-    return launch_fwd(cfg, P, packed, pl, fp, fp.S, st);
+    return launch_render_rays(cfg, P, packed, pl, rays, 0, rays->n_rays, w.folded, nullptr, nullptr, rgb, depth, acc, st);
 }
-
-int cnb_sm100_has_backward(void) { return 0; }
 
 int cnb_sm100_pipeline_timeouts(void) {
     unsigned int v = 0;
     if (cudaMemcpyFromSymbol(&v, umma::g_umma_timeout, sizeof(unsigned int)) != cudaSuccess) return -1;
-    return (int)v;
+    const int b = cnb_sm100_pipeline_timeouts_bwd();
+    return b < 0 ? b : (int)v | b;
 }

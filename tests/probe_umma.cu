@@ -220,6 +220,44 @@ int main() {
         }
         all &= run_case("mnmajor_sw128_n64", img, ops, 64, ref64, false);
     }
+    // ---- case 5: the wgrad stage layout: 64-row halves of [128 x 64] blocks (LBO = 8192) and an
+    //      MN-major 64-B-swizzle operand (the PE(viewdir) block, N = 32) ------------------------------
+    {
+        const int M = 128, N = 256, R = 64, ND = 32;
+        std::vector<float> At(R * M), Bt(R * N), Dt(R * ND);
+        for (auto& v : At) v = bf2f(f2bf(rnd(seed)));
+        for (auto& v : Bt) v = bf2f(f2bf(rnd(seed)));
+        for (auto& v : Dt) v = bf2f(f2bf(rnd(seed)));
+        std::vector<float> ref(M * N, 0.f), refd(M * ND, 0.f);
+        for (int m = 0; m < M; ++m) {
+            for (int n = 0; n < N; ++n) { double s = 0; for (int r = 0; r < R; ++r) s += (double)At[r * M + m] * Bt[r * N + n]; ref[m * N + n] = (float)s; }
+            for (int n = 0; n < ND; ++n) { double s = 0; for (int r = 0; r < R; ++r) s += (double)At[r * M + m] * Dt[r * ND + n]; refd[m * ND + n] = (float)s; }
+        }
+        // 8-KB half blocks: At -> 2, Bt -> 4, then the [64 x 32] SW64 block (4 KB)
+        const uint32_t a_base = 0, b_base = 2 * 8192, d_base = 6 * 8192;
+        std::vector<uint8_t> img(6 * 8192 + 4096, 0);
+        for (int r = 0; r < R; ++r) for (int m = 0; m < M; ++m) { uint16_t h = f2bf(At[r * M + m]); memcpy(&img[a_base + (m / 64) * 8192 + umma::sw128_offset(r, m % 64)], &h, 2); }
+        for (int r = 0; r < R; ++r) for (int n = 0; n < N; ++n) { uint16_t h = f2bf(Bt[r * N + n]); memcpy(&img[b_base + (n / 64) * 8192 + umma::sw128_offset(r, n % 64)], &h, 2); }
+        for (int r = 0; r < R; ++r) for (int n = 0; n < ND; ++n) { uint16_t h = f2bf(Dt[r * ND + n]); memcpy(&img[d_base + umma::sw64_offset(r, n)], &h, 2); }
+        std::vector<MmaOp> ops;
+        for (int ks = 0; ks < R / 16; ++ks) {
+            MmaOp o = {};
+            o.a_off = a_base + ks * 2048; o.a_lbo = 8192; o.a_sbo = 1024; o.a_swz = umma::SWZ_128B;
+            o.b_off = b_base + ks * 2048; o.b_lbo = 8192; o.b_sbo = 1024; o.b_swz = umma::SWZ_128B;
+            o.idesc = umma::make_idesc(128, 256, 1, 1); o.d_col = 0; o.accumulate = ks ? 1 : 0;
+            ops.push_back(o);
+        }
+        all &= run_case("mnmajor_halfblocks_lbo8k", img, ops, N, ref, false);
+        ops.clear();
+        for (int ks = 0; ks < R / 16; ++ks) {
+            MmaOp o = {};
+            o.a_off = a_base + ks * 2048; o.a_lbo = 8192; o.a_sbo = 1024; o.a_swz = umma::SWZ_128B;
+            o.b_off = d_base + ks * 1024; o.b_lbo = 4096; o.b_sbo = 512; o.b_swz = umma::SWZ_64B;
+            o.idesc = umma::make_idesc(128, 32, 1, 1); o.d_col = 0; o.accumulate = ks ? 1 : 0;
+            ops.push_back(o);
+        }
+        all &= run_case("mnmajor_sw64_n32", img, ops, ND, refd, false);
+    }
     printf("PROBE_SUMMARY %s\n", all ? "ALL_PASS" : "SOME_FAIL");
     return all ? 0 : 1;
 }

@@ -113,3 +113,130 @@ def test_fused_forward_bf16_broadcast_code_many_segments():
         rgb, depth, acc = cn.render(model, bundle, torch.from_numpy(scodes).cuda(), torch.from_numpy(tcodes).cuda())
     _no_timeouts()
     np.testing.assert_allclose(rgb.cpu().numpy(), np.concatenate([r["rgb"] for r in ref]), atol=ATOL, rtol=0)
+
+
+def _check_grads(got_flat, ref_flat, sc_g, sc_ref, tc_g, tc_ref, tol=4e-2, label=""):
+    """bf16 gradients: per-tensor max error relative to the tensor's max magnitude, and direction."""
+    worst = 0.0
+    o = 0
+    for key, shp in orc.param_shapes():
+        n = int(np.prod(shp))
+        g, r = got_flat[o:o + n], ref_flat[o:o + n]
+        e = U.rel_err(g, r)
+        cs = U.cosine(g, r)
+        worst = max(worst, e)
+        assert e < tol and cs > 0.999, (label, key, e, cs)
+        o += n
+    e_s, e_t = U.rel_err(sc_g, sc_ref), U.rel_err(tc_g, tc_ref)
+    print(f"{label}: worst param-grad rel err {worst:.3e}; d_shape {e_s:.3e}; d_tex {e_t:.3e}")
+    assert e_s < tol and e_t < tol, (label, e_s, e_t)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("c", [c for c in REN_CASES if c["n_codes"] == 1], ids=lambda c: f"r{c['k']}")
+def test_unfused_backward_bf16_vs_reference_fixture(c):
+    """model(...) -> volume_rendering -> loss.backward() on the tensor-core path."""
+    import codenerf_b200 as cn
+    k = c["k"]
+    inp = gu.render_case_inputs(c)
+    z = G_REN[f"r{k}_z"].view(np.float32)
+    ro, vd = orc.get_rays(c["H"], c["W"], inp["focal"], inp["c2w"], True)
+    xyz, vdr = orc.sample_from_rays(ro, vd, z)
+    model, flat = U.make_model("bf16")
+    R = inp["R"]
+    sc = torch.from_numpy(inp["shape_codes"]).cuda().requires_grad_()
+    tc = torch.from_numpy(inp["tex_codes"]).cuda().requires_grad_()
+    sig, col = model(torch.from_numpy(xyz).cuda(), torch.from_numpy(vdr).cuda(), sc, tc)
+    rgb, depth, acc = cn.volume_rendering_with_acc(sig, col, torch.from_numpy(z).cuda(), white_bg=c["white"])
+    tgt = torch.from_numpy(inp["targets"]).cuda()
+    loss = torch.mean((rgb - tgt) ** 2) + 1e-4 * torch.mean(torch.norm(sc, dim=-1) + torch.norm(tc, dim=-1)) + 0.37 * depth.mean()
+    loss.backward()
+    _no_timeouts()
+    ref_s, ref_t = G_REN[f"r{k}_d_shape"], G_REN[f"r{k}_d_tex"]
+    assert U.rel_err(sc.grad.cpu().numpy(), ref_s) < 4e-2, U.rel_err(sc.grad.cpu().numpy(), ref_s)
+    assert U.rel_err(tc.grad.cpu().numpy(), ref_t) < 4e-2
+    for t, (key, p) in enumerate(model.named_parameters()):
+        g = p.grad.cpu().numpy()
+        ref = G_REN[f"r{k}_g/full/{key}"] if g.ndim == 1 else G_REN[f"r{k}_g/head/{key}"]
+        got = g if g.ndim == 1 else g[:4]
+        e = U.rel_err(got, ref)
+        stat = G_REN[f"r{k}_g/stat/{key}"]
+        g64 = g.astype(np.float64).ravel()
+        probe = float(g64 @ gu.weight_probe(t, g64.size))
+        assert e < 5e-2, (key, e)
+        assert abs(np.abs(g64).sum() - stat[1]) < 3e-2 * stat[1] + 1e-9, (key, np.abs(g64).sum(), stat[1])
+        assert abs(probe - stat[2]) < 3e-2 * stat[1] + 1e-9, (key, probe, stat[2])
+
+
+def _fused_backward_case(N, H, W, n_seg, ray_count, cat, train_step):
+    import codenerf_b200 as cn
+    from codenerf_b200 import ops, _lib
+    model, flat, bundle, scodes, tcodes, zs, ref = _fused_case(N, H, W, n_seg, ray_count, cat, False)
+    tgt = syn.make_targets(13, n_seg * ray_count)
+    dP_ref = np.zeros(flat.size, np.float32)
+    ds_ref, dt_ref = [], []
+    for g in range(n_seg):
+        d_rgb = (2.0 * (ref[g]["rgb"] - tgt[g * ray_count:(g + 1) * ray_count]) / (3.0 * ray_count)).astype(np.float32)
+        dP, dsc, dtc = orc.render_backward(flat, ref[g], zs[g], scodes[g:g + 1], tcodes[g:g + 1], d_rgb, None, True)
+        dP_ref += dP
+        ds_ref.append(dsc)
+        dt_ref.append(dtc)
+    ds_ref, dt_ref = np.concatenate(ds_ref), np.concatenate(dt_ref)
+    t = torch.from_numpy(tgt).cuda()
+    if train_step:
+        params = model.param_list()
+        packed = model._packed.get(model._cfg, params)
+        rb = bundle.args(torch.from_numpy(scodes).cuda(), torch.from_numpy(tcodes).cuda())
+        dP = torch.zeros(flat.size, device="cuda")
+        rgb, depth, acc, sq, dsc, dtc = ops.render_train_step(model._cfg, params, packed, rb, _lib.PRECISION_BF16, t, 1.0, dP)
+        _no_timeouts()
+        rgb_ref = np.concatenate([r["rgb"] for r in ref])
+        np.testing.assert_allclose(rgb.cpu().numpy(), rgb_ref, atol=ATOL)
+        np.testing.assert_allclose(sq.cpu().numpy(), ((rgb_ref - tgt) ** 2).reshape(n_seg, -1).sum(1), rtol=2e-2)
+        _check_grads(dP.cpu().numpy(), dP_ref, dsc.cpu().numpy(), ds_ref, dtc.cpu().numpy(), dt_ref, label="train_step")
+    else:
+        sc = torch.from_numpy(scodes).cuda().requires_grad_()
+        tc = torch.from_numpy(tcodes).cuda().requires_grad_()
+        rgb, depth, acc = cn.render(model, bundle, sc, tc)
+        loss = ((rgb - t) ** 2).reshape(n_seg, -1).mean(1).sum()
+        loss.backward()
+        _no_timeouts()
+        _check_grads(U.named_grads_flat(model), dP_ref, sc.grad.cpu().numpy(), ds_ref, tc.grad.cpu().numpy(), dt_ref,
+                     label="autograd")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N,H,W,n_seg,ray_count,cat,train_step", [
+    (64, 32, 32, 3, 128, syn.SRN_CARS, False),
+    (64, 32, 32, 3, 128, syn.SRN_CARS, True),
+    (96, 24, 40, 2, 100, syn.SRN_CHAIRS, False),     # rows per code = 9600 = 75 tiles
+    (64, 64, 64, 2, 1000, syn.SRN_CARS, True),       # 1000 tiles: every CTA gets several
+    (40, 16, 16, 1, 77, syn.SRN_CARS, True),         # ragged tail tile
+])
+def test_fused_backward_bf16_vs_oracle(N, H, W, n_seg, ray_count, cat, train_step):
+    _fused_backward_case(N, H, W, n_seg, ray_count, cat, train_step)
+
+
+@pytest.mark.gpu
+def test_latent_only_backward_bf16():
+    """optimize.py's use: gradients for the codes only (no weight-gradient pass, no stash)."""
+    import codenerf_b200 as cn
+    N, H, W, n_seg, ray_count, cat = 64, 32, 32, 2, 256, syn.SRN_CHAIRS
+    model, flat, bundle, scodes, tcodes, zs, ref = _fused_case(N, H, W, n_seg, ray_count, cat, False)
+    for p in model.parameters():
+        p.requires_grad_(False)
+    tgt = syn.make_targets(13, n_seg * ray_count)
+    sc = torch.from_numpy(scodes).cuda().requires_grad_()
+    tc = torch.from_numpy(tcodes).cuda().requires_grad_()
+    rgb, depth, acc = cn.render(model, bundle, sc, tc)
+    ((rgb - torch.from_numpy(tgt).cuda()) ** 2).reshape(n_seg, -1).mean(1).sum().backward()
+    _no_timeouts()
+    ds_ref, dt_ref = [], []
+    for g in range(n_seg):
+        d_rgb = (2.0 * (ref[g]["rgb"] - tgt[g * ray_count:(g + 1) * ray_count]) / (3.0 * ray_count)).astype(np.float32)
+        _, dsc, dtc = orc.render_backward(flat, ref[g], zs[g], scodes[g:g + 1], tcodes[g:g + 1], d_rgb, None, True, want_param_grads=False)
+        ds_ref.append(dsc)
+        dt_ref.append(dtc)
+    assert U.rel_err(sc.grad.cpu().numpy(), np.concatenate(ds_ref)) < 4e-2
+    assert U.rel_err(tc.grad.cpu().numpy(), np.concatenate(dt_ref)) < 4e-2
+    assert all(p.grad is None for p in model.parameters())
