@@ -562,29 +562,55 @@ __global__ void k_head_wgrad(const uint8_t* __restrict__ stashA, uint32_t a_tile
                              const float* __restrict__ dspre, const float* __restrict__ d_rgbs, int64_t S,
                              int64_t n_tiles, float* __restrict__ d_wsigma, float* __restrict__ d_bsigma,
                              float* __restrict__ d_wrgb2, float* __restrict__ d_brgb2) {
-    const int t = threadIdx.x;                 // 256 threads
-    float as = 0.f, ar = 0.f, ag = 0.f, ab = 0.f, bs = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
+    // 8 warps; warp w streams rows w, w+8, ... of each tile.  Lane l owns one 16-byte chunk (8 columns) of the
+    // row: f chunk (blk = l>>3, chunk = l&7) and, for lanes < 16, the r1 chunk at the same coordinates.
+    __shared__ float red[8][32][33];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int blk = lane >> 3, chunk = lane & 7;
+    float af[8], ar[8], ag[8], ab[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { af[i] = 0.f; ar[i] = 0.f; ag[i] = 0.f; ab[i] = 0.f; }
+    float bs = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint8_t* base = stashA + (size_t)tile * a_tile_bytes;
         const int rows = (int)min((int64_t)kTileRows, S - tile * kTileRows);
-        for (int r = 0; r < rows; ++r) {
+        for (int r = warp; r < rows; r += 8) {
             const int64_t gr = tile * kTileRows + r;
             const float dsp = __ldg(dspre + gr);
-            const uint16_t fv = *reinterpret_cast<const uint16_t*>(base + f_off + (t >> 6) * kABlock + umma::sw128_offset(r, t & 63));
-            as = fmaf(dsp, __uint_as_float((uint32_t)fv << 16), as);
-            if (t < 128) {
-                const uint16_t rv = *reinterpret_cast<const uint16_t*>(base + r1_off + (t >> 6) * kABlock + umma::sw128_offset(r, t & 63));
-                const float h = __uint_as_float((uint32_t)rv << 16);
-                ar = fmaf(__ldg(d_rgbs + gr * 3 + 0), h, ar);
-                ag = fmaf(__ldg(d_rgbs + gr * 3 + 1), h, ag);
-                ab = fmaf(__ldg(d_rgbs + gr * 3 + 2), h, ab);
+            const float dr = __ldg(d_rgbs + gr * 3), dg = __ldg(d_rgbs + gr * 3 + 1), db = __ldg(d_rgbs + gr * 3 + 2);
+            const uint32_t off = blk * kABlock + r * 128 + ((chunk ^ (r & 7)) << 4);
+            const uint4 fw = __ldg(reinterpret_cast<const uint4*>(base + f_off + off));
+            af[0] = fmaf(dsp, bf_lo(fw.x), af[0]); af[1] = fmaf(dsp, bf_hi(fw.x), af[1]);
+            af[2] = fmaf(dsp, bf_lo(fw.y), af[2]); af[3] = fmaf(dsp, bf_hi(fw.y), af[3]);
+            af[4] = fmaf(dsp, bf_lo(fw.z), af[4]); af[5] = fmaf(dsp, bf_hi(fw.z), af[5]);
+            af[6] = fmaf(dsp, bf_lo(fw.w), af[6]); af[7] = fmaf(dsp, bf_hi(fw.w), af[7]);
+            if (lane < 16) {
+                const uint4 rw = __ldg(reinterpret_cast<const uint4*>(base + r1_off + off));
+                const float h[8] = {bf_lo(rw.x), bf_hi(rw.x), bf_lo(rw.y), bf_hi(rw.y),
+                                    bf_lo(rw.z), bf_hi(rw.z), bf_lo(rw.w), bf_hi(rw.w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { ar[i] = fmaf(dr, h[i], ar[i]); ag[i] = fmaf(dg, h[i], ag[i]); ab[i] = fmaf(db, h[i], ab[i]); }
             }
-            if (t == 0) { bs += dsp; b0 += __ldg(d_rgbs + gr * 3); b1 += __ldg(d_rgbs + gr * 3 + 1); b2 += __ldg(d_rgbs + gr * 3 + 2); }
+            if (lane == 0) { bs += dsp; b0 += dr; b1 += dg; b2 += db; }
         }
     }
-    atomicAdd(d_wsigma + t, as);
-    if (t < 128) { atomicAdd(d_wrgb2 + t, ar); atomicAdd(d_wrgb2 + 128 + t, ag); atomicAdd(d_wrgb2 + 256 + t, ab); }
-    if (t == 0) { atomicAdd(d_bsigma, bs); atomicAdd(d_brgb2, b0); atomicAdd(d_brgb2 + 1, b1); atomicAdd(d_brgb2 + 2, b2); }
+    // cross-warp reduction: value slot v of lane l -> red[warp][l][v]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        red[warp][lane][i] = af[i]; red[warp][lane][8 + i] = ar[i];
+        red[warp][lane][16 + i] = ag[i]; red[warp][lane][24 + i] = ab[i];
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 32 * 32; o += blockDim.x) {
+        const int l = o >> 5, v = o & 31;
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += red[w][l][v];
+        const int col = (l >> 3) * 64 + (l & 7) * 8 + (v & 7);
+        if (v < 8) atomicAdd(d_wsigma + col, s);
+        else if (l < 16) atomicAdd(d_wrgb2 + ((v >> 3) - 1) * 128 + col, s);
+    }
+    if (lane == 0) { atomicAdd(d_bsigma, bs); atomicAdd(d_brgb2, b0); atomicAdd(d_brgb2 + 1, b1); atomicAdd(d_brgb2 + 2, b2); }
 }
 
 // Bias gradients: db_l[n] += sum_codes colsum[code][l][n].
