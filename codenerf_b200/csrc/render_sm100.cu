@@ -139,70 +139,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
 
     if (warp == 0) {
         // ===== weight producer: TMA-engine bulk copies of stage images into the ring =====
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            for (int r = 0; r < rounds; ++r)
-                for (int l = 0; l < nl; ++l)
-                    for (int g = 0; g < 2; ++g) {
-                        if (2 * r + g >= T) continue;
-                        const FwdLayer& L = p.layers[l];
-                        const int n_main = L.n_kchunks * L.n_halves;
-                        const int nst = n_main + (L.has_dir ? L.n_halves : 0);
-                        for (int s = 0; s < nst; ++s) {
-                            umma::mbar_wait(&w_empty[stage], ph ^ 1);
-                            const uint32_t bytes = s < n_main ? kSlot : kSlot / 2;
-                            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
-                            umma::bulk_g2s(sW + stage * kSlot, p.packed + L.w_off + (size_t)s * kSlot, bytes,
-                                           &w_full[stage]);
-                            if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-                        }
-                    }
-        }
+        int stage = 0; uint32_t ph = 0;
+        for (int r = 0; r < rounds; ++r)
+            for (int l = 0; l < nl; ++l)
+                for (int g = 0; g < 2; ++g) {
+                    if (2 * r + g >= T) continue;
+                    const FwdLayer& L = p.layers[l];
+                    const int n_dir = L.has_dir ? L.n_halves : 0;
+                    produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
+                }
     } else if (warp == 1) {
-        // ===== MMA issuer: one thread drives the tensor core for both tiles =====
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            const uint32_t idesc = umma::make_idesc(128, 128, 0, 0);
-            for (int r = 0; r < rounds; ++r)
-                for (int l = 0; l < nl; ++l)
-                    for (int g = 0; g < 2; ++g) {
-                        if (2 * r + g >= T) continue;
-                        const FwdLayer& L = p.layers[l];
-                        umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
-                        umma::tc_fence_after();
-                        const uint32_t a_base = umma::smem_u32(sA0 + g * kATile);
-                        const uint32_t d_base = tmem + (uint32_t)g * 256u;
-                        for (int c = 0; c < L.n_kchunks; ++c)
-                            for (int h = 0; h < L.n_halves; ++h) {
-                                umma::mbar_wait(&w_full[stage], ph);
-                                umma::tc_fence_after();
-                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint64_t da = umma::make_sdesc(a_base + c * kABlock + ks * 32, 16, 1024, umma::SWZ_128B);
-                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 1024, umma::SWZ_128B);
-                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, (c | ks) ? 1u : 0u);
-                                }
-                                umma::mma_commit(&w_empty[stage]);
-                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-                            }
-                        if (L.has_dir)
-                            for (int h = 0; h < L.n_halves; ++h) {
-                                umma::mbar_wait(&w_full[stage], ph);
-                                umma::tc_fence_after();
-                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
-#pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {
-                                    const uint64_t da = umma::make_sdesc(a_base + 4 * kABlock + ks * 32, 16, 512, umma::SWZ_64B);
-                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 512, umma::SWZ_64B);
-                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, 1u);
-                                }
-                                umma::mma_commit(&w_empty[stage]);
-                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-                            }
-                        umma::mma_commit(&acc_full[g]);
-                    }
-        }
+        // ===== MMA issuer: one elected thread drives the tensor core for both tiles =====
+        int stage = 0; uint32_t ph = 0;
+        for (int r = 0; r < rounds; ++r)
+            for (int l = 0; l < nl; ++l)
+                for (int g = 0; g < 2; ++g) {
+                    if (2 * r + g >= T) continue;
+                    const FwdLayer& L = p.layers[l];
+                    umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
+                    umma::tc_fence_after();
+                    issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty,
+                               L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
+                }
     } else {
         // ===== compute groups: PE, per-layer epilogues (TMEM -> bias/ReLU -> bf16 operand), heads, compositing =====
         const int g = (warp - 2) >> 2;
@@ -212,6 +170,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         uint8_t* sA = sA0 + g * kATile;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
         const int N = p.rs.N;
+        uint32_t a8[8];     // shared address of each 16-byte chunk of this row inside K-block 0 (128-B swizzle)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a8[c] = umma::smem_u32(sA + row * 128 + ((c ^ (row & 7)) << 4));
         for (int r = 0; r < rounds; ++r) {
             const int t = 2 * r + g;
             if (t >= T) break;
@@ -247,62 +208,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&a_ready[g]);
 
-            float sig_pre = 0.f, cr = 0.f, cg = 0.f, cb = 0.f;
+            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull};
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
                 umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u);
                 umma::tc_fence_after();
                 const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
-                const int ncc = L.n_halves * 4;
-                const bool store = (l + 1 < nl);
-                for (int cc = 0; cc < ncc; ++cc) {
-                    uint32_t rr[32];
-                    umma::tmem_ld32(taddr + cc * 32, rr);
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const int col = cc * 32 + j8 * 8;
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-                        float v[8];
-                        v[0] = __uint_as_float(rr[j8 * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[j8 * 8 + 1]) + b0.y;
-                        v[2] = __uint_as_float(rr[j8 * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[j8 * 8 + 3]) + b0.w;
-                        v[4] = __uint_as_float(rr[j8 * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[j8 * 8 + 5]) + b1.y;
-                        v[6] = __uint_as_float(rr[j8 * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[j8 * 8 + 7]) + b1.w;
-                        if (L.relu) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                        }
-                        if (L.kind == 1) {          // sigma head on the fp32 feature (src/model.py:45)
-                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col));
-                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col + 4));
-                            sig_pre = fmaf(v[0], w0.x, sig_pre); sig_pre = fmaf(v[1], w0.y, sig_pre);
-                            sig_pre = fmaf(v[2], w0.z, sig_pre); sig_pre = fmaf(v[3], w0.w, sig_pre);
-                            sig_pre = fmaf(v[4], w1.x, sig_pre); sig_pre = fmaf(v[5], w1.y, sig_pre);
-                            sig_pre = fmaf(v[6], w1.z, sig_pre); sig_pre = fmaf(v[7], w1.w, sig_pre);
-                        } else if (L.kind == 2) {   // rgb.2 on the fp32 hidden (src/model.py:52)
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                cr = fmaf(v[i], __ldg(p.w_rgb2 + col + i), cr);
-                                cg = fmaf(v[i], __ldg(p.w_rgb2 + (kW / 2) + col + i), cg);
-                                cb = fmaf(v[i], __ldg(p.w_rgb2 + kW + col + i), cb);
-                            }
-                        }
-                        if (store) {
-                            const int blk = cc >> 1, chunk = ((cc & 1) << 2) + j8;
-                            st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4),
-                                         umma::pack_bf16(v[0], v[1]), umma::pack_bf16(v[2], v[3]),
-                                         umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
-                        }
-                    }
-                }
-                if (store) {
+                if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                else fwd_epilogue_layer<4, 2, false, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                if (l + 1 < nl) {
                     umma::tc_fence_before();
                     umma::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&a_ready[g]);
                 }
             }
+            float sig_pre, cr, cg, cb;
+            { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; unpk2(hacc.r2, a0, a1); cr = a0 + a1;
+              unpk2(hacc.g2, a0, a1); cg = a0 + a1; unpk2(hacc.b2, a0, a1); cb = a0 + a1; }
             // ---- heads -> outputs ----
             const float sigma = cnb_softplus(sig_pre + __ldg(p.b_sigma));
             cr += __ldg(p.b_rgb2 + 0); cg += __ldg(p.b_rgb2 + 1); cb += __ldg(p.b_rgb2 + 2);

@@ -4,6 +4,7 @@
 #include "render_sm100.cuh"
 #include "mlp_fp32.cuh"
 #include "umma.cuh"
+#include <type_traits>
 
 namespace sm100 {
 
@@ -35,6 +36,200 @@ struct FwdLayer {
 __device__ __forceinline__ void st_shared_v4(uint8_t* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(umma::smem_u32(p)), "r"(a), "r"(b), "r"(c), "r"(d)
                  : "memory");
+}
+
+// ---- packed fp32x2 / bf16x2 helpers (sm_100: FADD2 / FFMA2, F2FP with fused ReLU) -----------------
+__device__ __forceinline__ uint64_t pk2(uint32_t lo, uint32_t hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ uint64_t pk2f(float lo, float hi) { return pk2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpk2(uint64_t v, float& lo, float& hi) {
+    uint32_t a, b; asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v)); lo = __uint_as_float(a); hi = __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d;
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d;
+}
+// two fp32 -> packed bf16x2 (first value in the low half), optionally with ReLU fused into the conversion
+template <bool kRelu>
+__device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
+    float lo, hi; unpk2(v, lo, hi);
+    uint32_t d;
+    if (kRelu) asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+template <int kOff>
+__device__ __forceinline__ void st_shared_v4_off(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0 + %5], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "n"(kOff)
+                 : "memory");
+}
+
+// Accumulators of the narrow heads carried across a layer's epilogue as packed pairs.
+struct HeadAcc { uint64_t sig2, r2, g2, b2; };
+
+// Forward epilogue of 32 accumulator columns (one tcgen05.ld) of this thread's row:
+// + bias, [ReLU], [sigma / rgb head partial dot products in fp32], bf16 pack, swizzled store of
+// the next operand, [ReLU sign bits for the backward].   KIND: 0 hidden, 1 encoding_shape
+// (+ sigma head, no ReLU), 2 rgb.0 (+ rgb head).   a8[c] = shared address of 16-byte chunk c of
+// this row inside K-block 0.
+template <int CC, int KIND, bool STORE, bool MASK>
+__device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const float* __restrict__ bias,
+                                               const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
+                                               const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
+    constexpr bool RELU = (KIND != 1);
+    uint32_t sgn = 0u;
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+        constexpr int dummy = 0; (void)dummy;
+        const int col = CC * 32 + j8 * 8;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+        uint64_t v[4];
+        v[0] = fadd2(pk2(rr[j8 * 8 + 0], rr[j8 * 8 + 1]), pk2f(b0.x, b0.y));
+        v[1] = fadd2(pk2(rr[j8 * 8 + 2], rr[j8 * 8 + 3]), pk2f(b0.z, b0.w));
+        v[2] = fadd2(pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]), pk2f(b1.x, b1.y));
+        v[3] = fadd2(pk2(rr[j8 * 8 + 6], rr[j8 * 8 + 7]), pk2f(b1.z, b1.w));
+        if (MASK && RELU) {     // collect the sign bits of the pre-activations (column c -> bit 31 - c%32)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float lo, hi; unpk2(v[i], lo, hi);
+                sgn = __funnelshift_l(__float_as_uint(lo), sgn, 1);
+                sgn = __funnelshift_l(__float_as_uint(hi), sgn, 1);
+            }
+        }
+        if (KIND == 1) {        // sigma head on the fp32 feature (reference src/model.py:45)
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_sigma + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_sigma + col + 4));
+            acc.sig2 = ffma2(v[0], pk2f(w0.x, w0.y), acc.sig2); acc.sig2 = ffma2(v[1], pk2f(w0.z, w0.w), acc.sig2);
+            acc.sig2 = ffma2(v[2], pk2f(w1.x, w1.y), acc.sig2); acc.sig2 = ffma2(v[3], pk2f(w1.z, w1.w), acc.sig2);
+        } else if (KIND == 2) { // rgb.2 on the fp32 hidden (reference src/model.py:52)
+            uint64_t h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float lo, hi; unpk2(v[i], lo, hi); h[i] = pk2f(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_rgb2 + k * (kW / 2) + col));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_rgb2 + k * (kW / 2) + col + 4));
+                uint64_t& a = (k == 0) ? acc.r2 : (k == 1 ? acc.g2 : acc.b2);
+                a = ffma2(h[0], pk2f(w0.x, w0.y), a); a = ffma2(h[1], pk2f(w0.z, w0.w), a);
+                a = ffma2(h[2], pk2f(w1.x, w1.y), a); a = ffma2(h[3], pk2f(w1.z, w1.w), a);
+            }
+        }
+        if (STORE) {
+            constexpr int blk = CC >> 1;
+            const int chunk = ((CC & 1) << 2) + j8;
+            st_shared_v4_off<blk * kABlock>(a8[chunk], cvt_bf16x2<RELU>(v[0]), cvt_bf16x2<RELU>(v[1]),
+                                            cvt_bf16x2<RELU>(v[2]), cvt_bf16x2<RELU>(v[3]));
+        }
+    }
+    if (MASK && RELU) mscr[(size_t)CC * kTileRows] = ~sgn;   // bit set <=> pre-activation >= +0  (ReLU passes)
+}
+
+// A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.
+template <int NCC, int KIND, bool STORE, bool MASK>
+__device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
+                                                   const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
+                                                   const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
+    auto pair = [&](auto cc_tag) {
+        constexpr int CC = decltype(cc_tag)::value;
+        uint32_t ra[32], rb[32];
+        umma::tmem_ld32(taddr + CC * 32, ra);
+        umma::tmem_ld32(taddr + CC * 32 + 32, rb);
+        umma::tmem_ld_wait();
+        fwd_epilogue32<CC, KIND, STORE, MASK>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC + 1, KIND, STORE, MASK>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    };
+    pair(std::integral_constant<int, 0>{});
+    pair(std::integral_constant<int, 2>{});
+    if constexpr (NCC == 8) {
+        pair(std::integral_constant<int, 4>{});
+        pair(std::integral_constant<int, 6>{});
+    }
+}
+
+// ---- warp-uniform pipeline roles ------------------------------------------------------------------
+// Both helpers are executed by a WHOLE warp (so addresses / descriptors live in uniform registers);
+// a single elected lane issues the asynchronous instructions.
+
+// Stream `n_stages` consecutive weight stage images (the last `n_small` of them half-size) into the ring.
+__device__ __forceinline__ void produce_stages(const uint8_t* __restrict__ src, int n_stages, int n_small, uint8_t* sW,
+                                               uint64_t* w_full, uint64_t* w_empty, int& stage, uint32_t& ph) {
+    for (int s = 0; s < n_stages; ++s) {
+        umma::mbar_wait(&w_empty[stage], ph ^ 1);
+        if (umma::elect_one()) {
+            const uint32_t bytes = s < n_stages - n_small ? kSlot : kSlot / 2;
+            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
+            umma::bulk_g2s(sW + stage * kSlot, src + (size_t)s * kSlot, bytes, &w_full[stage]);
+        }
+        __syncwarp();
+        if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+    }
+}
+
+// Issue one GEMM of one tile: D[128 x (128*n_halves)] = A[128 x 64*n_kchunks (+32)] . B^T.
+// A = K-blocks 0.. of the tile's operand buffer (+ the PE(viewdir) block); B = ring stages in the
+// order (chunk, half).  With two halves the pair of adjacent stages is one N = 256 operand.
+__device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t d_base, uint8_t* sW, uint64_t* w_full,
+                                           uint64_t* w_empty, int n_kchunks, int n_halves, int has_dir, int& stage,
+                                           uint32_t& ph, uint64_t* done_bar) {
+    const uint64_t dA = umma::make_sdesc(a_base, 16, 1024, umma::SWZ_128B);
+    const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
+    if (n_halves == 2) {
+        const uint32_t idesc = umma::make_idesc(128, 256, 0, 0);
+        for (int c = 0; c < n_kchunks; ++c) {
+            umma::mbar_wait(&w_full[stage], ph);
+            umma::mbar_wait(&w_full[stage + 1], ph);
+            umma::tc_fence_after();
+            if (umma::elect_one()) {
+                const uint64_t da = dA + (uint64_t)((c * kABlock) >> 4);
+                const uint64_t db = dB + (uint64_t)((stage * kSlot) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma::mma_bf16(d_base, da + ks * 2, db + ks * 2, idesc, (c | ks) ? 1u : 0u);
+                umma::mma_commit(&w_empty[stage]);
+                umma::mma_commit(&w_empty[stage + 1]);
+            }
+            __syncwarp();
+            stage += 2;
+            if (stage == kNumStages) { stage = 0; ph ^= 1; }
+        }
+    } else {
+        const uint32_t idesc = umma::make_idesc(128, 128, 0, 0);
+        for (int c = 0; c < n_kchunks; ++c) {
+            umma::mbar_wait(&w_full[stage], ph);
+            umma::tc_fence_after();
+            if (umma::elect_one()) {
+                const uint64_t da = dA + (uint64_t)((c * kABlock) >> 4);
+                const uint64_t db = dB + (uint64_t)((stage * kSlot) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) umma::mma_bf16(d_base, da + ks * 2, db + ks * 2, idesc, (c | ks) ? 1u : 0u);
+                umma::mma_commit(&w_empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+        }
+    }
+    if (has_dir) {
+        const uint32_t idesc = umma::make_idesc(128, 128, 0, 0);
+        const uint64_t dAd = umma::make_sdesc(a_base + 4 * kABlock, 16, 512, umma::SWZ_64B);
+        const uint64_t dBd = umma::make_sdesc(umma::smem_u32(sW), 16, 512, umma::SWZ_64B);
+        for (int h = 0; h < n_halves; ++h) {
+            umma::mbar_wait(&w_full[stage], ph);
+            umma::tc_fence_after();
+            if (umma::elect_one()) {
+                const uint64_t db = dBd + (uint64_t)((stage * kSlot) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) umma::mma_bf16(d_base + h * 128, dAd + ks * 2, db + ks * 2, idesc, 1u);
+                umma::mma_commit(&w_empty[stage]);
+            }
+            __syncwarp();
+            if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+        }
+    }
+    if (umma::elect_one()) umma::mma_commit(done_bar);
+    __syncwarp();
 }
 
 // PE of one row into the operand blocks -- reference src/model.py:4-7 (x, sines, cosines).
