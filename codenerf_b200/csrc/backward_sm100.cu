@@ -66,6 +66,59 @@ __device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
+// Input-gradient epilogue of 32 accumulator columns: [+ dsigma_pre * w_sigma] [* ReLU mask bits] -> bf16 operand.
+template <int CC, bool HAS_MASK, bool ADD_SIGMA>
+__device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const uint32_t (&a8)[8], uint32_t mw,
+                                               uint64_t dsp2, const float* __restrict__ w_sigma) {
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+        const int col = CC * 32 + j8 * 8;
+        uint64_t v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = pk2(rr[j8 * 8 + 2 * i], rr[j8 * 8 + 2 * i + 1]);
+        if (ADD_SIGMA) {
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_sigma + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_sigma + col + 4));
+            v[0] = ffma2(dsp2, pk2f(w0.x, w0.y), v[0]); v[1] = ffma2(dsp2, pk2f(w0.z, w0.w), v[1]);
+            v[2] = ffma2(dsp2, pk2f(w1.x, w1.y), v[2]); v[3] = ffma2(dsp2, pk2f(w1.z, w1.w), v[3]);
+        }
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (HAS_MASK) {
+                float lo, hi; unpk2(v[i], lo, hi);
+                lo = (mw & (0x80000000u >> (j8 * 8 + 2 * i))) ? lo : 0.f;
+                hi = (mw & (0x80000000u >> (j8 * 8 + 2 * i + 1))) ? hi : 0.f;
+                w[i] = cvt_bf16x2<false>(pk2f(lo, hi));
+            } else {
+                w[i] = cvt_bf16x2<false>(v[i]);
+            }
+        }
+        constexpr int blk = CC >> 1;
+        const int chunk = ((CC & 1) << 2) + j8;
+        st_shared_v4_off<blk * kABlock>(a8[chunk], w[0], w[1], w[2], w[3]);
+    }
+}
+template <bool HAS_MASK, bool ADD_SIGMA>
+__device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_t (&a8)[8], const uint32_t* mscr,
+                                                   uint64_t dsp2, const float* __restrict__ w_sigma) {
+    auto pair = [&](auto cc_tag) {
+        constexpr int CC = decltype(cc_tag)::value;
+        uint32_t ra[32], rb[32];
+        umma::tmem_ld32(taddr + CC * 32, ra);
+        umma::tmem_ld32(taddr + CC * 32 + 32, rb);
+        const uint32_t m0 = HAS_MASK ? mscr[(size_t)CC * kTileRows] : 0xffffffffu;
+        const uint32_t m1 = HAS_MASK ? mscr[(size_t)(CC + 1) * kTileRows] : 0xffffffffu;
+        umma::tmem_ld_wait();
+        bwd_epilogue32<CC, HAS_MASK, ADD_SIGMA>(ra, a8, m0, dsp2, w_sigma);
+        bwd_epilogue32<CC + 1, HAS_MASK, ADD_SIGMA>(rb, a8, m1, dsp2, w_sigma);
+    };
+    pair(std::integral_constant<int, 0>{});
+    pair(std::integral_constant<int, 2>{});
+    pair(std::integral_constant<int, 4>{});
+    pair(std::integral_constant<int, 6>{});
+}
+
 __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -106,76 +159,35 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 
     if (warp == 0) {
         // ===== weight producer =====
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            for (int r = 0; r < rounds; ++r)
-                for (int op = 0; op < n_ops; ++op)
-                    for (int g = 0; g < 2; ++g) {
-                        if (2 * r + g >= T) continue;
-                        uint32_t w_off; int n_main, n_dir;
-                        if (op < nl) {
-                            const FwdLayer& L = p.layers[op];
-                            w_off = L.w_off; n_main = L.n_kchunks * L.n_halves; n_dir = L.has_dir ? L.n_halves : 0;
-                        } else {
-                            const BwdStep& B = p.steps[op - nl + 1];
-                            w_off = B.w_off; n_main = B.n_kchunks * 2; n_dir = 0;
-                        }
-                        for (int s = 0; s < n_main + n_dir; ++s) {
-                            umma::mbar_wait(&w_empty[stage], ph ^ 1);
-                            const uint32_t bytes = s < n_main ? kSlot : kSlot / 2;
-                            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
-                            umma::bulk_g2s(sW + stage * kSlot, p.packed + w_off + (size_t)s * kSlot, bytes, &w_full[stage]);
-                            if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-                        }
+        int stage = 0; uint32_t ph = 0;
+        for (int r = 0; r < rounds; ++r)
+            for (int op = 0; op < n_ops; ++op)
+                for (int g = 0; g < 2; ++g) {
+                    if (2 * r + g >= T) continue;
+                    if (op < nl) {
+                        const FwdLayer& L = p.layers[op];
+                        const int n_dir = L.has_dir ? L.n_halves : 0;
+                        produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
+                    } else {
+                        const BwdStep& B = p.steps[op - nl + 1];
+                        produce_stages(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph);
                     }
-        }
+                }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            const uint32_t idesc = umma::make_idesc(128, 128, 0, 0);
-            for (int r = 0; r < rounds; ++r)
-                for (int op = 0; op < n_ops; ++op)
-                    for (int g = 0; g < 2; ++g) {
-                        if (2 * r + g >= T) continue;
-                        int n_kchunks, n_halves, has_dir;
-                        if (op < nl) { n_kchunks = p.layers[op].n_kchunks; n_halves = p.layers[op].n_halves; has_dir = p.layers[op].has_dir; }
-                        else { n_kchunks = p.steps[op - nl + 1].n_kchunks; n_halves = 2; has_dir = 0; }
-                        umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u);
-                        umma::tc_fence_after();
-                        const uint32_t a_base = umma::smem_u32(sA0 + g * kATile);
-                        const uint32_t d_base = tmem + (uint32_t)g * 256u;
-                        for (int c = 0; c < n_kchunks; ++c)
-                            for (int h = 0; h < n_halves; ++h) {
-                                umma::mbar_wait(&w_full[stage], ph);
-                                umma::tc_fence_after();
-                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
-#pragma unroll
-                                for (int ks = 0; ks < 4; ++ks) {
-                                    const uint64_t da = umma::make_sdesc(a_base + c * kABlock + ks * 32, 16, 1024, umma::SWZ_128B);
-                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 1024, umma::SWZ_128B);
-                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, (c | ks) ? 1u : 0u);
-                                }
-                                umma::mma_commit(&w_empty[stage]);
-                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-                            }
-                        if (has_dir)
-                            for (int h = 0; h < n_halves; ++h) {
-                                umma::mbar_wait(&w_full[stage], ph);
-                                umma::tc_fence_after();
-                                const uint32_t b_addr = umma::smem_u32(sW + stage * kSlot);
-#pragma unroll
-                                for (int ks = 0; ks < 2; ++ks) {
-                                    const uint64_t da = umma::make_sdesc(a_base + 4 * kABlock + ks * 32, 16, 512, umma::SWZ_64B);
-                                    const uint64_t db = umma::make_sdesc(b_addr + ks * 32, 16, 512, umma::SWZ_64B);
-                                    umma::mma_bf16(d_base + h * 128, da, db, idesc, 1u);
-                                }
-                                umma::mma_commit(&w_empty[stage]);
-                                if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-                            }
-                        umma::mma_commit(&acc_full[g]);
-                    }
-        }
+        int stage = 0; uint32_t ph = 0;
+        for (int r = 0; r < rounds; ++r)
+            for (int op = 0; op < n_ops; ++op)
+                for (int g = 0; g < 2; ++g) {
+                    if (2 * r + g >= T) continue;
+                    int n_kchunks, n_halves, has_dir;
+                    if (op < nl) { n_kchunks = p.layers[op].n_kchunks; n_halves = p.layers[op].n_halves; has_dir = p.layers[op].has_dir; }
+                    else { n_kchunks = p.steps[op - nl + 1].n_kchunks; n_halves = 2; has_dir = 0; }
+                    umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u);
+                    umma::tc_fence_after();
+                    issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                               n_halves, has_dir, stage, ph, &acc_full[g]);
+                }
     } else if (warp >= 10) {
         // ===== auxiliary warps: operand stash (TMA bulk stores) and column sums of every dY =====
         const int g = warp - 10;
@@ -237,6 +249,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         uint8_t* sA = sA0 + g * kATile;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
         const int N = p.rs.N;
+        uint32_t a8[8];       // shared address of each 16-byte chunk of this row inside K-block 0
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a8[c] = umma::smem_u32(sA + row * 128 + ((c ^ (row & 7)) << 4));
         uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
         uint32_t opc = 0;     // accumulator phases consumed
         uint32_t* mscr = p.mask_scratch + ((size_t)(blockIdx.x * 2 + g) * nl) * 8 * kTileRows + row;
@@ -284,58 +299,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             publish(true);
 
             // ---- forward chain (recompute) ----
-            float sig_pre = 0.f;
+            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull};
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
                 umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
                 umma::tc_fence_after();
                 const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
-                const int ncc = L.n_halves * 4;
                 const bool last = (l + 1 == nl);
                 const bool store = !last || p.stash;
                 if (store) wait_buf_free();
-                for (int cc = 0; cc < ncc; ++cc) {
-                    uint32_t rr[32];
-                    umma::tmem_ld32(taddr + cc * 32, rr);
-                    umma::tmem_ld_wait();
-                    uint32_t mw = 0u;
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const int col = cc * 32 + j8 * 8;
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
-                        float v[8];
-                        v[0] = __uint_as_float(rr[j8 * 8 + 0]) + b0.x; v[1] = __uint_as_float(rr[j8 * 8 + 1]) + b0.y;
-                        v[2] = __uint_as_float(rr[j8 * 8 + 2]) + b0.z; v[3] = __uint_as_float(rr[j8 * 8 + 3]) + b0.w;
-                        v[4] = __uint_as_float(rr[j8 * 8 + 4]) + b1.x; v[5] = __uint_as_float(rr[j8 * 8 + 5]) + b1.y;
-                        v[6] = __uint_as_float(rr[j8 * 8 + 6]) + b1.z; v[7] = __uint_as_float(rr[j8 * 8 + 7]) + b1.w;
-                        if (L.relu) {
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                v[i] = fmaxf(v[i], 0.f);
-                                // mask bit (31 - column % 32): top bit of (bits + 0x7fffffff) is set iff v > 0
-                                mw = __funnelshift_l(__float_as_uint(v[i]) + 0x7fffffffu, mw, 1);
-                            }
-                        }
-                        if (L.kind == 1) {
-                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col));
-                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col + 4));
-                            sig_pre = fmaf(v[0], w0.x, sig_pre); sig_pre = fmaf(v[1], w0.y, sig_pre);
-                            sig_pre = fmaf(v[2], w0.z, sig_pre); sig_pre = fmaf(v[3], w0.w, sig_pre);
-                            sig_pre = fmaf(v[4], w1.x, sig_pre); sig_pre = fmaf(v[5], w1.y, sig_pre);
-                            sig_pre = fmaf(v[6], w1.z, sig_pre); sig_pre = fmaf(v[7], w1.w, sig_pre);
-                        }
-                        if (store) {
-                            const int blk = cc >> 1, chunk = ((cc & 1) << 2) + j8;
-                            st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4),
-                                         umma::pack_bf16(v[0], v[1]), umma::pack_bf16(v[2], v[3]),
-                                         umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
-                        }
-                    }
-                    if (L.relu) mscr[((size_t)l * 8 + cc) * kTileRows] = mw;
-                }
+                uint32_t* ml = mscr + (size_t)l * 8 * kTileRows;
+                if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                else if (store) fwd_epilogue_layer<4, 0, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                else fwd_epilogue_layer<4, 0, false, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
                 if (store) publish(!last);
             }
+            float sig_pre;
+            { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
             const float x = sig_pre + __ldg(p.b_sigma);
             const float ex = expf(x);
             const float dspre = x > 20.f ? ds : ds * ex / (ex + 1.f);      // softplus backward (ATen form)
@@ -343,63 +324,44 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 
             // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
             wait_buf_free();
-            uint32_t mlast = 0u;
+            {
+                const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
+                uint32_t mlast = 0u;
 #pragma unroll
-            for (int c8 = 0; c8 < 16; ++c8) {
-                if ((c8 & 3) == 0) mlast = mscr[((size_t)(nl - 1) * 8 + (c8 >> 2)) * kTileRows];
-                float v[8];
+                for (int c8 = 0; c8 < 16; ++c8) {
+                    if ((c8 & 3) == 0) mlast = mscr[((size_t)(nl - 1) * 8 + (c8 >> 2)) * kTileRows];
+                    const int col = c8 * 8;
+                    uint32_t w[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int col = c8 * 8 + i;
-                    float a = dcr * __ldg(p.w_rgb2 + col);
-                    a = fmaf(dcg, __ldg(p.w_rgb2 + (kW / 2) + col), a);
-                    a = fmaf(dcb, __ldg(p.w_rgb2 + kW + col), a);
-                    const uint32_t keep = (uint32_t)((int32_t)(mlast << (col & 31)) >> 31);
-                    v[i] = __uint_as_float(__float_as_uint(a) & keep);
+                    for (int hh = 0; hh < 2; ++hh) {
+                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_rgb2 + col + hh * 4));
+                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_rgb2 + (kW / 2) + col + hh * 4));
+                        const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.w_rgb2 + kW + col + hh * 4));
+                        uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
+                        uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
+                        float f0, f1, f2, f3; unpk2(v0, f0, f1); unpk2(v1, f2, f3);
+                        const int pos = (col & 31) + hh * 4;
+                        f0 = (mlast & (0x80000000u >> (pos + 0))) ? f0 : 0.f; f1 = (mlast & (0x80000000u >> (pos + 1))) ? f1 : 0.f;
+                        f2 = (mlast & (0x80000000u >> (pos + 2))) ? f2 : 0.f; f3 = (mlast & (0x80000000u >> (pos + 3))) ? f3 : 0.f;
+                        w[hh * 2 + 0] = cvt_bf16x2<false>(pk2f(f0, f1)); w[hh * 2 + 1] = cvt_bf16x2<false>(pk2f(f2, f3));
+                    }
+                    if (c8 < 8) st_shared_v4_off<0>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                    else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
                 }
-                const int blk = c8 >> 3, chunk = c8 & 7;
-                st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4), umma::pack_bf16(v[0], v[1]),
-                             umma::pack_bf16(v[2], v[3]), umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
             }
             publish(ns > 1);
 
             // ---- input-gradient chain ----
+            const uint64_t dsp2 = pk2f(dspre, dspre);
             for (int s = 1; s < ns; ++s) {
                 const BwdStep& B = p.steps[s];
                 umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
                 umma::tc_fence_after();
                 wait_buf_free();
-                const bool has_mask = B.mask_layer >= 0;
-                for (int cc = 0; cc < 8; ++cc) {
-                    uint32_t rr[32];
-                    umma::tmem_ld32(taddr + cc * 32, rr);
-                    const uint32_t mw = has_mask ? mscr[((size_t)B.mask_layer * 8 + cc) * kTileRows] : 0xffffffffu;
-                    umma::tmem_ld_wait();
-#pragma unroll
-                    for (int j8 = 0; j8 < 4; ++j8) {
-                        const int col = cc * 32 + j8 * 8;
-                        float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(rr[j8 * 8 + i]);
-                        if (B.add_sigma) {
-                            const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col));
-                            const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_sigma + col + 4));
-                            v[0] = fmaf(dspre, w0.x, v[0]); v[1] = fmaf(dspre, w0.y, v[1]);
-                            v[2] = fmaf(dspre, w0.z, v[2]); v[3] = fmaf(dspre, w0.w, v[3]);
-                            v[4] = fmaf(dspre, w1.x, v[4]); v[5] = fmaf(dspre, w1.y, v[5]);
-                            v[6] = fmaf(dspre, w1.z, v[6]); v[7] = fmaf(dspre, w1.w, v[7]);
-                        }
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const uint32_t keep = (uint32_t)((int32_t)(mw << (j8 * 8 + i)) >> 31);
-                            v[i] = __uint_as_float(__float_as_uint(v[i]) & keep);
-                        }
-                        const int blk = cc >> 1, chunk = ((cc & 1) << 2) + j8;
-                        st_shared_v4(sA + blk * kABlock + row * 128 + ((chunk ^ (row & 7)) << 4),
-                                     umma::pack_bf16(v[0], v[1]), umma::pack_bf16(v[2], v[3]),
-                                     umma::pack_bf16(v[4], v[5]), umma::pack_bf16(v[6], v[7]));
-                    }
-                }
+                const uint32_t* ml = mscr + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
+                if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, p.w_sigma);
+                else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, p.w_sigma);
+                else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, p.w_sigma);
                 publish(s + 1 < ns);
             }
         }
