@@ -51,6 +51,14 @@ struct BwdParams {
     int stash;                      // 1: stream operand tiles + dspre to HBM (training)
     uint8_t *stashA, *stashD;
     float* dspre;                   // [S] d(loss)/d(sigma pre-activation)
+    // fused compositing (+ loss) when every tile holds whole rays (128 % N == 0): the seeds are made in-kernel
+    int fuse_comp;                  // 0: seeds from d_sigmas / d_rgbs; 1: from d_rgb_rays / d_depth_rays; 2: from target (L2)
+    int white_bg;
+    int64_t n_rays_total;
+    const float *b_rgb2, *d_rgb_rays, *d_depth_rays, *target;   // per-ray arrays indexed by global ray
+    float loss_scale;
+    float *out_rgb, *out_depth, *out_acc, *sq_err;
+    float* drgb_out;                // [S,3] per-sample d rgb written for the head weight gradient (fused + stash)
     uint32_t a_slot[kMaxLayers + 1];// byte offset in a tile's A stash of the input of layer l; [n_layers] = rgb.2 input
     uint32_t dir_slot;
     uint32_t d_slot[kMaxLayers];    // byte offset in a tile's dY stash of dY_l
@@ -65,6 +73,105 @@ __device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) {
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// Forward compositing, loss seed and reverse-mode compositing of ONE ray by one warp, on the tile's
+// per-sample (sigma, r, g, b) in shared memory -- reference src/utils.py:34-47 and its autograd, the L2
+// seed of src/trainer.py:75.  N <= 128 (up to 4 samples per lane).  Writes per-sample seeds to `seed`.
+__device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, const float4* smp, float4* seed, int64_t gray,
+                                                  int lane) {
+    const int N = p.rs.N;
+    const int per = N >> 5;          // N in {32, 64, 128}
+    const int i0 = lane * per;
+    const bool live = gray < p.n_rays_total;
+    const int64_t seg = (live ? gray : 0) / p.rs.rays_per_segment;
+    const float* z = p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0);
+    float alpha[4], tt[4], dl[4], ex[4], zz[4];
+    float4 s[4];
+    float tl = 1.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < per) {
+            const int i = i0 + j;
+            s[j] = smp[i];
+            zz[j] = __ldg(z + i);
+            dl[j] = (i + 1 < N) ? (__ldg(z + i + 1) - zz[j]) : 1e10f;
+            ex[j] = expf(-s[j].x * dl[j]);
+            alpha[j] = 1.f - ex[j];
+            tt[j] = 1.f - alpha[j] + 1e-10f;
+            tl *= tt[j];
+        }
+    }
+    // exclusive transmittance product across lanes
+    float incl = tl;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const float up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl *= up; }
+    float T0 = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) T0 = 1.f;
+    float Tj[4], cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, ws = 0.f;
+    {
+        float T = T0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < per) {
+                Tj[j] = T;
+                const float w = alpha[j] * T;
+                cr += w * s[j].y; cg += w * s[j].z; cb += w * s[j].w; dep += w * zz[j]; ws += w;
+                T *= tt[j];
+            }
+        }
+    }
+    cr = warp_sum_f(cr); cg = warp_sum_f(cg); cb = warp_sum_f(cb); dep = warp_sum_f(dep); ws = warp_sum_f(ws);
+    if (p.white_bg) { cr = cr + 1.f - ws; cg = cg + 1.f - ws; cb = cb + 1.f - ws; }
+    // seed of the ray
+    float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f;
+    if (live) {
+        if (p.fuse_comp == 2) {
+            const float er = cr - __ldg(p.target + gray * 3), eg = cg - __ldg(p.target + gray * 3 + 1),
+                        eb = cb - __ldg(p.target + gray * 3 + 2);
+            const float k = 2.f / (3.f * (float)p.rs.rays_per_segment) * p.loss_scale;
+            gr = er * k; gg = eg * k; gb = eb * k;
+            if (lane == 0 && p.sq_err) atomicAdd(p.sq_err + seg, er * er + eg * eg + eb * eb);
+        } else {
+            gr = __ldg(p.d_rgb_rays + gray * 3); gg = __ldg(p.d_rgb_rays + gray * 3 + 1); gb = __ldg(p.d_rgb_rays + gray * 3 + 2);
+            if (p.d_depth_rays) gd = __ldg(p.d_depth_rays + gray);
+        }
+        if (lane == 0) {
+            if (p.out_rgb) { p.out_rgb[gray * 3] = cr; p.out_rgb[gray * 3 + 1] = cg; p.out_rgb[gray * 3 + 2] = cb; }
+            if (p.out_depth) p.out_depth[gray] = dep;
+            if (p.out_acc) p.out_acc[gray] = ws;
+        }
+    }
+    // reverse mode: aT_i = g_i alpha_i + t_i aT_{i+1}; d alpha_i = (g_i - aT_{i+1}) T_i   (division free)
+    const float bg = p.white_bg ? 1.f : 0.f;
+    float gsm[4];
+    float A = 1.f, Bc = 0.f;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+        if (j < per) {
+            gsm[j] = gr * (s[j].y - bg) + gg * (s[j].z - bg) + gb * (s[j].w - bg) + gd * zz[j];
+            Bc = gsm[j] * alpha[j] + tt[j] * Bc;
+            A = tt[j] * A;
+        }
+    }
+    float sA = A, sB = Bc;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float oA = __shfl_down_sync(0xffffffffu, sA, d);
+        const float oB = __shfl_down_sync(0xffffffffu, sB, d);
+        if (lane + d < 32) { sB = sA * oB + sB; sA = sA * oA; }
+    }
+    float aT_next = __shfl_down_sync(0xffffffffu, sB, 1);
+    if (lane == 31) aT_next = 0.f;
+#pragma unroll
+    for (int j = 3; j >= 0; --j) {
+        if (j < per) {
+            const float w = alpha[j] * Tj[j];
+            const float a_alpha = (gsm[j] - aT_next) * Tj[j];
+            seed[i0 + j] = make_float4(a_alpha * dl[j] * ex[j], w * gr, w * gg, w * gb);
+            aT_next = gsm[j] * alpha[j] + aT_next * tt[j];
+        }
+    }
+}
 
 // Input-gradient epilogue of 32 accumulator columns: [+ dsigma_pre * w_sigma] [* ReLU mask bits] -> bf16 operand.
 template <int CC, bool HAS_MASK, bool ADD_SIGMA>
@@ -132,6 +239,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     uint64_t* aux_ready = acc_full + 2;          // [2] a tile operand was (re)written (every phase)
     uint64_t* buf_free = aux_ready + 2;          // [2] aux warp finished reading the operand buffer
     uint32_t* tmem_slot = (uint32_t*)(buf_free + 2);
+    float4* sSamp = (float4*)(tmem_slot + 4);      // [2][128] per-sample (sigma, r, g, b) of the group's tile
+    float4* sSeed = sSamp + 2 * kTileRows;         // [2][128] per-sample (d sigma, d r, d g, d b)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = p.n_layers, ns = p.n_steps;
@@ -287,8 +396,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                     for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + lrow * 3 + k); dir[k] = __ldg(p.viewdir + lrow * 3 + k); }
                 }
-                ds = __ldg(p.d_sigmas + lrow);
-                dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
+                if (!p.fuse_comp) {
+                    ds = __ldg(p.d_sigmas + lrow);
+                    dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
+                }
             }
             int64_t code = 0;
             if (p.n_codes > 1) { code = (p.row_offset + (tile0 + t) * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
@@ -311,6 +422,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 uint32_t* ml = mscr + (size_t)l * 8 * kTileRows;
                 if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
                 else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                else if (p.fuse_comp) {
+                    if (store) fwd_epilogue_layer<4, 2, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                    else fwd_epilogue_layer<4, 2, false, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                }
                 else if (store) fwd_epilogue_layer<4, 0, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
                 else fwd_epilogue_layer<4, 0, false, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
                 if (store) publish(!last);
@@ -318,9 +433,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             float sig_pre;
             { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
             const float x = sig_pre + __ldg(p.b_sigma);
+            if (p.fuse_comp) {
+                // per-ray compositing, loss seed and compositing backward inside the tile
+                float a0, a1, cr, cg, cb;
+                unpk2(hacc.r2, a0, a1); cr = a0 + a1 + __ldg(p.b_rgb2 + 0);
+                unpk2(hacc.g2, a0, a1); cg = a0 + a1 + __ldg(p.b_rgb2 + 1);
+                unpk2(hacc.b2, a0, a1); cb = a0 + a1 + __ldg(p.b_rgb2 + 2);
+                float4* samp = sSamp + g * kTileRows;
+                float4* seed = sSeed + g * kTileRows;
+                samp[row] = make_float4(cnb_softplus(x), cr, cg, cb);
+                umma::named_bar_sync(1 + g, 128);
+                const int rays_in_tile = kTileRows / N;
+                const int64_t ray_base = (p.row_offset + (tile0 + t) * kTileRows) / N;
+                for (int k = (warp - 2) & 3; k < rays_in_tile; k += 4)
+                    composite_fwd_bwd(p, samp + k * N, seed + k * N, ray_base + k, lane);
+                umma::named_bar_sync(1 + g, 128);
+                const float4 sd = seed[row];
+                ds = sd.x; dcr = sd.y; dcg = sd.z; dcb = sd.w;
+            }
             const float ex = expf(x);
             const float dspre = x > 20.f ? ds : ds * ex / (ex + 1.f);      // softplus backward (ATen form)
-            if (p.stash && valid) p.dspre[lrow] = dspre;
+            if (p.stash && valid) {
+                p.dspre[lrow] = dspre;
+                if (p.fuse_comp) { p.drgb_out[lrow * 3] = dcr; p.drgb_out[lrow * 3 + 1] = dcg; p.drgb_out[lrow * 3 + 2] = dcb; }
+            }
 
             // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
             wait_buf_free();
@@ -431,16 +567,17 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                int pi; int64_t hb, he;
-                wg_item(p, item, pi, hb, he);
-                const WgProblem& P = p.prob[pi];
-                const uint32_t bytes = P.m_blocks * 8192u + (P.is_dir ? 4096u : P.n_blocks * 8192u);
-                for (int64_t h = hb; h < he; ++h) {
-                    const int64_t tile = h >> 1; const uint32_t half = (uint32_t)(h & 1);
-                    umma::mbar_wait(&empty[stage], ph ^ 1);
+        // ===== producer: half-tile operand slices of the stash, TMA bulk copies =====
+        int stage = 0; uint32_t ph = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            int pi; int64_t hb, he;
+            wg_item(p, item, pi, hb, he);
+            const WgProblem& P = p.prob[pi];
+            const uint32_t bytes = P.m_blocks * 8192u + (P.is_dir ? 4096u : P.n_blocks * 8192u);
+            for (int64_t h = hb; h < he; ++h) {
+                const int64_t tile = h >> 1; const uint32_t half = (uint32_t)(h & 1);
+                umma::mbar_wait(&empty[stage], ph ^ 1);
+                if (umma::elect_one()) {
                     umma::mbar_arrive_expect_tx(&full[stage], bytes);
                     uint8_t* dst = smem + stage * kWgStage;
                     const uint8_t* srcD = p.stashD + (size_t)tile * p.d_tile_bytes + P.d_off + half * 8192u;
@@ -451,37 +588,43 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
                         const uint8_t* srcA = p.stashA + (size_t)tile * p.a_tile_bytes + P.a_off + half * 8192u;
                         for (int b = 0; b < P.n_blocks; ++b) umma::bulk_g2s(dst + 32768 + b * 8192, srcA + (size_t)b * kABlock, 8192, &full[stage]);
                     }
-                    if (++stage == kWgStages) { stage = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0; uint32_t it = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-                int pi; int64_t hb, he;
-                wg_item(p, item, pi, hb, he);
-                const WgProblem& P = p.prob[pi];
-                const uint32_t idesc = umma::make_idesc(128, P.is_dir ? 32 : P.n_blocks * 64, 1, 1);
-                if (it > 0) { umma::mbar_wait(acc_free, (it - 1) & 1u); umma::tc_fence_after(); }
-                for (int64_t h = hb; h < he; ++h) {
-                    umma::mbar_wait(&full[stage], ph);
-                    umma::tc_fence_after();
-                    const uint32_t sb = umma::smem_u32(smem + stage * kWgStage);
+        // ===== MMA issuer (whole warp runs the loop, one elected lane issues) =====
+        int stage = 0; uint32_t ph = 0; uint32_t it = 0;
+        const uint64_t dA0 = umma::make_sdesc(umma::smem_u32(smem), 8192, 1024, umma::SWZ_128B);
+        const uint64_t dB0 = umma::make_sdesc(umma::smem_u32(smem) + 32768, 8192, 1024, umma::SWZ_128B);
+        const uint64_t dD0 = umma::make_sdesc(umma::smem_u32(smem) + 32768, 4096, 512, umma::SWZ_64B);
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+            int pi; int64_t hb, he;
+            wg_item(p, item, pi, hb, he);
+            const WgProblem& P = p.prob[pi];
+            const uint32_t idesc = umma::make_idesc(128, P.is_dir ? 32 : P.n_blocks * 64, 1, 1);
+            const int mhalves = P.m_blocks / 2;
+            if (it > 0) { umma::mbar_wait(acc_free, (it - 1) & 1u); umma::tc_fence_after(); }
+            for (int64_t h = hb; h < he; ++h) {
+                umma::mbar_wait(&full[stage], ph);
+                umma::tc_fence_after();
+                if (umma::elect_one()) {
+                    const uint64_t so = (uint64_t)((stage * kWgStage) >> 4);
+                    const uint32_t first = (h > hb) ? 1u : 0u;
 #pragma unroll
                     for (int ks = 0; ks < 4; ++ks) {
-                        const uint64_t db = P.is_dir ? umma::make_sdesc(sb + 32768 + ks * 1024, 4096, 512, umma::SWZ_64B)
-                                                     : umma::make_sdesc(sb + 32768 + ks * 2048, 8192, 1024, umma::SWZ_128B);
-                        for (int mh = 0; mh < P.m_blocks / 2; ++mh) {
-                            const uint64_t da = umma::make_sdesc(sb + mh * 16384 + ks * 2048, 8192, 1024, umma::SWZ_128B);
-                            umma::mma_bf16(tmem + mh * 256, da, db, idesc, (h > hb || ks > 0) ? 1u : 0u);
-                        }
+                        const uint64_t db = P.is_dir ? dD0 + so + (uint64_t)(ks * 64) : dB0 + so + (uint64_t)(ks * 128);
+                        for (int mh = 0; mh < mhalves; ++mh)
+                            umma::mma_bf16(tmem + mh * 256, dA0 + so + (uint64_t)(mh * 1024 + ks * 128), db, idesc, first | (ks > 0 ? 1u : 0u));
                     }
                     umma::mma_commit(&empty[stage]);
-                    if (++stage == kWgStages) { stage = 0; ph ^= 1; }
                 }
-                umma::mma_commit(acc_done);
+                __syncwarp();
+                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
             }
+            if (umma::elect_one()) umma::mma_commit(acc_done);
+            __syncwarp();
         }
     } else {
         const int q = warp & 3;
@@ -689,10 +832,17 @@ int num_sms() {
 }
 
 // K2 (+ K3 and head gradients when d_params != null) over launch-relative rows [0, S).
+struct FuseArgs {     // compositing (+ loss) fused into K2: per-ray arrays are indexed by global ray
+    int kind;         // 1: seeds from d_rgb / d_depth, 2: L2 loss against target
+    int white_bg; int64_t n_rays_total;
+    const float *d_rgb, *d_depth, *target; float loss_scale;
+    float *rgb, *depth, *acc, *sq_err;
+};
+
 int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* packed, const Plan& pl, BwdWorkspace& w,
                 int mode, const CnbRaySource* rs, const float* xyz, const float* viewdir, int64_t S, int64_t row_offset,
                 int n_codes, int64_t rows_per_code, const float* d_sigmas, const float* d_rgbs, float* d_params,
-                cudaStream_t st) {
+                cudaStream_t st, const FuseArgs* fuse = nullptr) {
     CnbLayout L; cnb_make_layout(c, &L);
     const StashLayout sl = make_stash_layout(pl);
     BwdParams bp = {};
@@ -720,6 +870,14 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
     bp.mask_scratch = w.masks; bp.colsum = w.colsum;
     bp.stash = d_params ? 1 : 0; bp.stashA = w.stashA; bp.stashD = w.stashD; bp.dspre = w.dspre;
+    bp.b_rgb2 = P[L.i_rgb2 + 1];
+    if (fuse) {
+        bp.fuse_comp = fuse->kind; bp.white_bg = fuse->white_bg; bp.n_rays_total = fuse->n_rays_total;
+        bp.d_rgb_rays = fuse->d_rgb; bp.d_depth_rays = fuse->d_depth; bp.target = fuse->target; bp.loss_scale = fuse->loss_scale;
+        bp.out_rgb = fuse->rgb; bp.out_depth = fuse->depth; bp.out_acc = fuse->acc; bp.sq_err = fuse->sq_err;
+        bp.drgb_out = w.drgb;
+        d_rgbs = w.drgb;          // the head weight gradient reads the per-sample seeds K2 writes
+    }
     for (int l = 0; l <= nl; ++l) bp.a_slot[l] = sl.a_slot[l];
     for (int l = 0; l < nl; ++l) bp.d_slot[l] = sl.d_slot[l];
     bp.dir_slot = sl.dir_slot; bp.a_tile_bytes = sl.a_tile_bytes; bp.d_tile_bytes = sl.d_tile_bytes;
@@ -728,7 +886,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     const int64_t tiles = (S + kTileRows - 1) / kTileRows;
     const int64_t units = (tiles + 1) / 2;
     const int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256;
+    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256 + 4 * kTileRows * sizeof(float4);
     CNB_CUDA_TRY(cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cnb_prof_begin(CNB_K_BWD, st);
     k_mlp_bwd<<<grid, kBwdThreads, smem, st>>>(bp);
@@ -864,6 +1022,7 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
         while (sub_rays > 1 && (sub_rays * N) % kTileRows != 0) --sub_rays;
         if ((sub_rays * N) % kTileRows != 0 && sub_rays < rays->n_rays) return CNB_E_UNSUPPORTED;
     }
+    if ((kTileRows % N) == 0 && sub_rays < rays->n_rays) sub_rays -= sub_rays % (kTileRows / N);
     sub_rows = sub_rays * N;
     BwdWorkspace w;
     const size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr);
@@ -875,9 +1034,20 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
     if (mode == 2 && sq_err)
         CNB_CUDA_TRY(cudaMemsetAsync(sq_err, 0, sizeof(float) * (size_t)(rays->n_rays / rays->rays_per_segment), st));
     CnbRaySource rs = cnb_make_ray_source(rays);
+    const bool fuse = (kTileRows % N) == 0 && (sub_rays * N) % kTileRows == 0;
     for (int64_t r0 = 0; r0 < rays->n_rays; r0 += sub_rays) {
         const int64_t nr = rays->n_rays - r0 < sub_rays ? rays->n_rays - r0 : sub_rays;
-        // forward (spilling per-sample sigma / rgb for the compositing backward)
+        if (fuse) {
+            // every 128-row tile holds whole rays: compositing, the loss seed and its backward run inside K2
+            FuseArgs fa = {};
+            fa.kind = mode; fa.white_bg = rays->white_bg; fa.n_rays_total = rays->n_rays;
+            fa.d_rgb = d_rgb; fa.d_depth = d_depth; fa.target = target; fa.loss_scale = loss_scale;
+            fa.rgb = rgb; fa.depth = depth; fa.acc = acc; fa.sq_err = mode == 2 ? sq_err : nullptr;
+            CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 0, &rs, nullptr, nullptr, nr * N, r0 * N, rays->n_codes,
+                                rays->n_codes > 1 ? rows_per_code : S, nullptr, nullptr, d_params, st, &fa));
+            continue;
+        }
+        // general N: forward kernel (spilling per-sample sigma / rgb), compositing backward, then K2
         float* o_rgb = rgb ? rgb : w.ray_rgb - r0 * 3;
         float* o_depth = depth ? depth : w.ray_depth - r0;
         float* o_acc = acc ? acc : w.ray_acc - r0;
