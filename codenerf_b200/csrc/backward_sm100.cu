@@ -679,24 +679,32 @@ __global__ void k_head_wgrad(const uint8_t* __restrict__ stashA, uint32_t a_tile
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint8_t* base = stashA + (size_t)tile * a_tile_bytes;
         const int rows = (int)min((int64_t)kTileRows, S - tile * kTileRows);
-        for (int r = warp; r < rows; r += 8) {
-            const int64_t gr = tile * kTileRows + r;
-            const float dsp = __ldg(dspre + gr);
-            const float dr = __ldg(d_rgbs + gr * 3), dg = __ldg(d_rgbs + gr * 3 + 1), db = __ldg(d_rgbs + gr * 3 + 2);
-            const uint32_t off = blk * kABlock + r * 128 + ((chunk ^ (r & 7)) << 4);
-            const uint4 fw = __ldg(reinterpret_cast<const uint4*>(base + f_off + off));
-            af[0] = fmaf(dsp, bf_lo(fw.x), af[0]); af[1] = fmaf(dsp, bf_hi(fw.x), af[1]);
-            af[2] = fmaf(dsp, bf_lo(fw.y), af[2]); af[3] = fmaf(dsp, bf_hi(fw.y), af[3]);
-            af[4] = fmaf(dsp, bf_lo(fw.z), af[4]); af[5] = fmaf(dsp, bf_hi(fw.z), af[5]);
-            af[6] = fmaf(dsp, bf_lo(fw.w), af[6]); af[7] = fmaf(dsp, bf_hi(fw.w), af[7]);
-            if (lane < 16) {
-                const uint4 rw = __ldg(reinterpret_cast<const uint4*>(base + r1_off + off));
-                const float h[8] = {bf_lo(rw.x), bf_hi(rw.x), bf_lo(rw.y), bf_hi(rw.y),
-                                    bf_lo(rw.z), bf_hi(rw.z), bf_lo(rw.w), bf_hi(rw.w)};
+        for (int r0 = warp; r0 < rows; r0 += 32) {        // 4 rows in flight per warp
+            uint4 fw[4], rw[4]; float dsp[4], dr[4], dg[4], db[4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { ar[i] = fmaf(dr, h[i], ar[i]); ag[i] = fmaf(dg, h[i], ag[i]); ab[i] = fmaf(db, h[i], ab[i]); }
+            for (int u = 0; u < 4; ++u) {
+                const int r = r0 + u * 8;
+                const bool ok = r < rows;
+                const int64_t gr = tile * kTileRows + (ok ? r : 0);
+                const uint32_t off = blk * kABlock + (ok ? r : 0) * 128 + ((chunk ^ (r & 7)) << 4);
+                fw[u] = __ldg(reinterpret_cast<const uint4*>(base + f_off + off));
+                rw[u] = lane < 16 ? __ldg(reinterpret_cast<const uint4*>(base + r1_off + off)) : make_uint4(0, 0, 0, 0);
+                dsp[u] = ok ? __ldg(dspre + gr) : 0.f;
+                dr[u] = ok ? __ldg(d_rgbs + gr * 3) : 0.f; dg[u] = ok ? __ldg(d_rgbs + gr * 3 + 1) : 0.f;
+                db[u] = ok ? __ldg(d_rgbs + gr * 3 + 2) : 0.f;
             }
-            if (lane == 0) { bs += dsp; b0 += dr; b1 += dg; b2 += db; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                af[0] = fmaf(dsp[u], bf_lo(fw[u].x), af[0]); af[1] = fmaf(dsp[u], bf_hi(fw[u].x), af[1]);
+                af[2] = fmaf(dsp[u], bf_lo(fw[u].y), af[2]); af[3] = fmaf(dsp[u], bf_hi(fw[u].y), af[3]);
+                af[4] = fmaf(dsp[u], bf_lo(fw[u].z), af[4]); af[5] = fmaf(dsp[u], bf_hi(fw[u].z), af[5]);
+                af[6] = fmaf(dsp[u], bf_lo(fw[u].w), af[6]); af[7] = fmaf(dsp[u], bf_hi(fw[u].w), af[7]);
+                const float h[8] = {bf_lo(rw[u].x), bf_hi(rw[u].x), bf_lo(rw[u].y), bf_hi(rw[u].y),
+                                    bf_lo(rw[u].z), bf_hi(rw[u].z), bf_lo(rw[u].w), bf_hi(rw[u].w)};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { ar[i] = fmaf(dr[u], h[i], ar[i]); ag[i] = fmaf(dg[u], h[i], ag[i]); ab[i] = fmaf(db[u], h[i], ab[i]); }
+                if (lane == 0) { bs += dsp[u]; b0 += dr[u]; b1 += dg[u]; b2 += db[u]; }
+            }
         }
     }
     // cross-warp reduction: value slot v of lane l -> red[warp][l][v]
@@ -937,7 +945,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     CNB_LAUNCH_CHECK();
     // narrow heads (sigma, rgb.2): inputs f (input of encoding_viewdir) and the rgb.0 hidden
     int l_vd = 1 + c->shape_blocks + 1;
-    const int hgrid = (int)(tiles < 4 * sms ? tiles : 4 * sms);
+    const int hgrid = (int)(tiles < 6 * sms ? tiles : 6 * sms);
     k_head_wgrad<<<hgrid, 256, 0, st>>>(w.stashA, sl.a_tile_bytes, sl.a_slot[l_vd], sl.a_slot[nl], w.dspre, d_rgbs, S, tiles,
                                        d_params + L.sigma_w, d_params + L.sigma_b, d_params + L.rgb2_w,
                                        d_params + L.rgb2_b);
