@@ -208,14 +208,14 @@ __device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const u
 }
 template <bool HAS_MASK, bool ADD_SIGMA>
 __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_t (&a8)[8], const uint32_t* mscr,
-                                                   uint64_t dsp2, const float* __restrict__ w_sigma) {
+                                                   uint64_t dsp2, const float* __restrict__ w_sigma, uint64_t pol) {
     auto pair = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
         uint32_t ra[32], rb[32];
         umma::tmem_ld32(taddr + CC * 32, ra);
         umma::tmem_ld32(taddr + CC * 32 + 32, rb);
-        const uint32_t m0 = HAS_MASK ? mscr[(size_t)CC * kTileRows] : 0xffffffffu;
-        const uint32_t m1 = HAS_MASK ? mscr[(size_t)(CC + 1) * kTileRows] : 0xffffffffu;
+        const uint32_t m0 = HAS_MASK ? umma::ld_global_hint(mscr + (size_t)CC * kTileRows, pol) : 0xffffffffu;
+        const uint32_t m1 = HAS_MASK ? umma::ld_global_hint(mscr + (size_t)(CC + 1) * kTileRows, pol) : 0xffffffffu;
         umma::tmem_ld_wait();
         bwd_epilogue32<CC, HAS_MASK, ADD_SIGMA>(ra, a8, m0, dsp2, w_sigma);
         bwd_epilogue32<CC + 1, HAS_MASK, ADD_SIGMA>(rb, a8, m1, dsp2, w_sigma);
@@ -302,6 +302,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const int g = warp - 10;
         const uint8_t* sA = sA0 + g * kATile;
         uint32_t ap = 0;
+        const uint64_t pol_stream = umma::l2_policy_evict_first();   // the stash is written once and read by a later kernel
         const int n_phases = nl + 1 + ns;
         for (int r = 0; r < rounds; ++r) {
             const int t = 2 * r + g;
@@ -323,9 +324,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
                 }
                 if (p.stash && lane == 0) {
-                    umma::bulk_s2g(dst, sA, (uint32_t)blocks * kABlock);
+                    umma::bulk_s2g_hint(dst, sA, (uint32_t)blocks * kABlock, pol_stream);
                     if (phs == 0)
-                        umma::bulk_s2g(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock);
+                        umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
                     umma::bulk_commit();
                 }
                 if (out_layer >= 0 && lane < blocks * 8) {
@@ -361,6 +362,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         uint32_t a8[8];       // shared address of each 16-byte chunk of this row inside K-block 0
 #pragma unroll
         for (int c = 0; c < 8; ++c) a8[c] = umma::smem_u32(sA + row * 128 + ((c ^ (row & 7)) << 4));
+        const uint64_t pol_keep = umma::l2_policy_evict_last();   // ReLU masks: written now, re-read ~50 us later
         uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
         uint32_t opc = 0;     // accumulator phases consumed
         uint32_t* mscr = p.mask_scratch + ((size_t)(blockIdx.x * 2 + g) * nl) * 8 * kTileRows + row;
@@ -410,7 +412,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             publish(true);
 
             // ---- forward chain (recompute) ----
-            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull};
+            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, pol_keep};
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
                 umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
@@ -465,7 +467,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 uint32_t mlast = 0u;
 #pragma unroll
                 for (int c8 = 0; c8 < 16; ++c8) {
-                    if ((c8 & 3) == 0) mlast = mscr[((size_t)(nl - 1) * 8 + (c8 >> 2)) * kTileRows];
+                    if ((c8 & 3) == 0) mlast = umma::ld_global_hint(mscr + ((size_t)(nl - 1) * 8 + (c8 >> 2)) * kTileRows, pol_keep);
                     const int col = c8 * 8;
                     uint32_t w[4];
 #pragma unroll
@@ -495,9 +497,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 umma::tc_fence_after();
                 wait_buf_free();
                 const uint32_t* ml = mscr + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
-                if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, p.w_sigma);
-                else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, p.w_sigma);
-                else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, p.w_sigma);
+                if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, p.w_sigma, pol_keep);
+                else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, p.w_sigma, pol_keep);
+                else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, p.w_sigma, pol_keep);
                 publish(s + 1 < ns);
             }
         }

@@ -10,6 +10,7 @@
 //
 // Reference semantics: src/model.py:36-53 (network), src/utils.py:10-47 (rays, sampling,
 // compositing).  See DESIGN.md for the tile / pipeline design and the roofline arithmetic.
+#include <cstdlib>
 #include "sm100_common.cuh"
 
 using namespace sm100;
@@ -89,6 +90,9 @@ __device__ __forceinline__ void composite_ray(const FwdParams& p, const float4* 
     }
 }
 
+// CG = 1: one CTA per SM, M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2), tcgen05 cta_group::2 with M = 256:
+// each CTA streams half of every weight chunk, halving L2 and shared-memory operand traffic per row.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constant__ FwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -100,42 +104,53 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     uint64_t* w_empty = bars + kNumStages;
     uint64_t* a_ready = bars + 2 * kNumStages;
     uint64_t* acc_full = a_ready + 2;
-    uint32_t* tmem_slot = (uint32_t*)(acc_full + 2);
+    uint64_t* w_full_peer = acc_full + 2;        // [kNumStages] (leader of a CTA pair): the peer's half has landed
+    uint32_t* tmem_slot = (uint32_t*)(w_full_peer + kNumStages);
     volatile int* final_count = (volatile int*)(tmem_slot + 2);
+    const uint32_t rank = CG == 2 ? umma::cluster_ctarank() : 0u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = p.n_layers;
 
     // ---- this CTA's contiguous share of the work -------------------------------------------
-    int64_t row0, nrows, ray0 = 0;
-    if (p.mode == 0) {
-        const int64_t base = p.n_rays / gridDim.x, rem = p.n_rays % gridDim.x;
-        ray0 = (int64_t)blockIdx.x * base + min((int64_t)blockIdx.x, rem);
-        const int64_t nr = base + ((int64_t)blockIdx.x < rem ? 1 : 0);
-        row0 = ray0 * p.rs.N; nrows = nr * p.rs.N;
-    } else {
-        const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
-        const int64_t base = tiles / gridDim.x, rem = tiles % gridDim.x;
-        const int64_t t0 = (int64_t)blockIdx.x * base + min((int64_t)blockIdx.x, rem);
-        const int64_t nt = base + ((int64_t)blockIdx.x < rem ? 1 : 0);
-        row0 = t0 * kTileRows;
-        nrows = min(p.S - row0, nt * kTileRows);
-        if (nrows < 0) nrows = 0;
+    int64_t row0 = 0, nrows = 0, ray0 = 0;
+    int T = 0;                                   // tile slots of this CTA (pair-uniform when CG == 2)
+    for (int who = 0; who < CG; ++who) {         // who == 0: this CTA; who == 1: its pair partner (only its tile count matters)
+        const int64_t b = who == 0 ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x ^ 1u);
+        int64_t r0_, n_, ray0_ = 0;
+        if (p.mode == 0) {
+            const int64_t base = p.n_rays / gridDim.x, rem = p.n_rays % gridDim.x;
+            ray0_ = b * base + min(b, rem);
+            const int64_t nr = base + (b < rem ? 1 : 0);
+            r0_ = ray0_ * p.rs.N; n_ = nr * p.rs.N;
+        } else {
+            const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
+            const int64_t base = tiles / gridDim.x, rem = tiles % gridDim.x;
+            const int64_t t0 = b * base + min(b, rem);
+            const int64_t nt = base + (b < rem ? 1 : 0);
+            r0_ = t0 * kTileRows;
+            n_ = min(p.S - r0_, nt * kTileRows);
+            if (n_ < 0) n_ = 0;
+        }
+        if (who == 0) { row0 = r0_; nrows = n_; ray0 = ray0_; }
+        T = max(T, (int)((n_ + kTileRows - 1) / kTileRows));
     }
-    const int T = (int)((nrows + kTileRows - 1) / kTileRows);
     const int rounds = (T + 1) >> 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], 1); }
-        for (int g = 0; g < 2; ++g) { umma::mbar_init(&a_ready[g], 4); umma::mbar_init(&acc_full[g], 1); }
+        for (int i = 0; i < kNumStages; ++i) umma::mbar_init(&w_full_peer[i], 1);
+        for (int g = 0; g < 2; ++g) { umma::mbar_init(&a_ready[g], 4 * CG); umma::mbar_init(&acc_full[g], 1); }
         final_count[0] = 0; final_count[1] = 0;
         umma::fence_mbar_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (CG == 2) umma::tmem_alloc2(tmem_slot, 512); else umma::tmem_alloc(tmem_slot, 512); }
     umma::tc_fence_before();
-    __syncthreads();
+    if (CG == 2) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // a_ready lives in the leader CTA: the partner's compute warps arrive on it remotely
+    const uint32_t a_ready_addr0 = CG == 2 ? umma::mapa(umma::smem_u32(&a_ready[0]), 0) : 0u;
 
     if (warp == 0) {
         // ===== weight producer: TMA-engine bulk copies of stage images into the ring =====
@@ -146,7 +161,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     if (2 * r + g >= T) continue;
                     const FwdLayer& L = p.layers[l];
                     const int n_dir = L.has_dir ? L.n_halves : 0;
-                    produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
+                    if (CG == 2) produce_stages_2cta(p.packed + L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
+                    else produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
                 }
     } else if (warp == 1) {
         // ===== MMA issuer: one elected thread drives the tensor core for both tiles =====
@@ -156,10 +172,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 for (int g = 0; g < 2; ++g) {
                     if (2 * r + g >= T) continue;
                     const FwdLayer& L = p.layers[l];
-                    umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
+                    if (CG == 2 && rank != 0) {      // partner CTA: only reports its weight halves
+                        forward_stages_2cta(L.n_kchunks + (L.has_dir ? 1 : 0), w_full, w_full_peer, stage, ph);
+                        continue;
+                    }
+                    if (CG == 2) umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
+                    else umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
                     umma::tc_fence_after();
-                    issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty,
-                               L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
+                    if (CG == 2)
+                        issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_full_peer,
+                                        w_empty, L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
+                    else
+                        issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty,
+                                   L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
                 }
     } else {
         // ===== compute groups: PE, per-layer epilogues (TMEM -> bias/ReLU -> bf16 operand), heads, compositing =====
@@ -206,9 +231,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) umma::mbar_arrive(&a_ready[g]);
+            if (lane == 0) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
 
-            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull};
+            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, 0ull};
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
                 umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u);
@@ -221,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     umma::tc_fence_before();
                     umma::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) umma::mbar_arrive(&a_ready[g]);
+                    if (lane == 0) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
                 }
             }
             float sig_pre, cr, cg, cb;
@@ -263,8 +288,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         }
     }
     umma::tc_fence_before();
-    __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+    if (CG == 2) umma::cluster_sync_all(); else __syncthreads();
+    if (warp == 1) { if (CG == 2) umma::tmem_dealloc2(tmem, 512); else umma::tmem_dealloc(tmem, 512); }
 }
 
 // ---------------------------------------------------------------------------
@@ -386,9 +411,26 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     int64_t units = (total_rows + 2 * kTileRows - 1) / (2 * kTileRows);
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-    CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();
+    if (use_pairs && grid >= 2) {
+        grid &= ~1;
+        CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cnb_prof_begin(CNB_K_FWD, st);
+        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_render_fwd<2>, fp);
+        cnb_prof_end(CNB_K_FWD, st);
+        if (e != cudaSuccess) return (int)e;
+        CNB_LAUNCH_CHECK();
+        return CNB_OK;
+    }
+    CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cnb_prof_begin(CNB_K_FWD, st);
-    k_render_fwd<<<grid, kThreads, smem, st>>>(fp);
+    k_render_fwd<1><<<grid, kThreads, smem, st>>>(fp);
     cnb_prof_end(CNB_K_FWD, st);
     CNB_LAUNCH_CHECK();
     return CNB_OK;

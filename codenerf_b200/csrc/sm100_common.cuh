@@ -68,7 +68,7 @@ __device__ __forceinline__ void st_shared_v4_off(uint32_t addr, uint32_t a, uint
 }
 
 // Accumulators of the narrow heads carried across a layer's epilogue as packed pairs.
-struct HeadAcc { uint64_t sig2, r2, g2, b2; };
+struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 
 // Forward epilogue of 32 accumulator columns (one tcgen05.ld) of this thread's row:
 // + bias, [ReLU], [sigma / rgb head partial dot products in fp32], bf16 pack, swizzled store of
@@ -125,7 +125,7 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
                                             cvt_bf16x2<RELU>(v[2]), cvt_bf16x2<RELU>(v[3]));
         }
     }
-    if (MASK && RELU) mscr[(size_t)CC * kTileRows] = ~sgn;   // bit set <=> pre-activation >= +0  (ReLU passes)
+    if (MASK && RELU) umma::st_global_hint(mscr + (size_t)CC * kTileRows, ~sgn, acc.mask_policy);   // bit set <=> pre-activation >= +0
 }
 
 // A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.
@@ -229,6 +229,77 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t d_base, uin
         }
     }
     if (umma::elect_one()) umma::mma_commit(done_bar);
+    __syncwarp();
+}
+
+// ---- CTA-pair (cta_group::2) versions: each CTA streams HALF of every weight chunk (its 128 of the 256
+// output columns, or 64 of 128), the leader issues M = 256 MMAs covering one tile of each CTA ------------
+// stages of one GEMM for CTA `rank`: chunk c -> image (c * n_halves + rank) [n_halves == 2], or the
+// rank-th 8 KB of image c [n_halves == 1]; the PE(viewdir) chunk -> image (n_main + rank), 8 KB.
+__device__ __forceinline__ void produce_stages_2cta(const uint8_t* __restrict__ src, int n_kchunks, int n_halves, int has_dir,
+                                                    uint32_t rank, uint8_t* sW, uint64_t* w_full, uint64_t* w_empty,
+                                                    int& stage, uint32_t& ph) {
+    const int n = n_kchunks + (has_dir ? 1 : 0);
+    for (int c = 0; c < n; ++c) {
+        umma::mbar_wait(&w_empty[stage], ph ^ 1);
+        if (umma::elect_one()) {
+            const bool dir = c >= n_kchunks;
+            const uint32_t bytes = (dir || n_halves == 1) ? kSlot / 2 : kSlot;
+            const uint8_t* s = dir ? src + (size_t)(n_kchunks * n_halves + rank) * kSlot
+                                   : (n_halves == 2 ? src + (size_t)(c * 2 + rank) * kSlot : src + (size_t)c * kSlot + rank * (kSlot / 2));
+            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
+            umma::bulk_g2s(sW + stage * kSlot, s, bytes, &w_full[stage]);
+        }
+        __syncwarp();
+        if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+    }
+}
+// peer CTA: tell the leader when this CTA's half of each stage has landed
+__device__ __forceinline__ void forward_stages_2cta(int n_stages, uint64_t* w_full, uint64_t* w_full_peer, int& stage, uint32_t& ph) {
+    for (int c = 0; c < n_stages; ++c) {
+        umma::mbar_wait(&w_full[stage], ph);
+        if (umma::elect_one()) umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&w_full_peer[stage]), 0));
+        __syncwarp();
+        if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+    }
+}
+// leader CTA: issue one GEMM for the pair's two tiles (M = 256)
+__device__ __forceinline__ void issue_gemm_2cta(uint32_t a_base, uint32_t d_base, uint8_t* sW, uint64_t* w_full,
+                                                uint64_t* w_full_peer, uint64_t* w_empty, int n_kchunks, int n_halves,
+                                                int has_dir, int& stage, uint32_t& ph, uint64_t* done_bar) {
+    const uint64_t dA = umma::make_sdesc(a_base, 16, 1024, umma::SWZ_128B);
+    const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
+    const uint32_t idesc = umma::make_idesc(256, n_halves * 128, 0, 0);
+    for (int c = 0; c < n_kchunks; ++c) {
+        umma::mbar_wait(&w_full[stage], ph);
+        umma::mbar_wait_cluster(&w_full_peer[stage], ph);
+        umma::tc_fence_after();
+        if (umma::elect_one()) {
+            const uint64_t da = dA + (uint64_t)((c * kABlock) >> 4);
+            const uint64_t db = dB + (uint64_t)((stage * kSlot) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_2cta(d_base, da + ks * 2, db + ks * 2, idesc, (c | ks) ? 1u : 0u);
+            umma::mma_commit_2cta(&w_empty[stage], 3);
+        }
+        __syncwarp();
+        if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+    }
+    if (has_dir) {
+        const uint64_t dAd = umma::make_sdesc(a_base + 4 * kABlock, 16, 512, umma::SWZ_64B);
+        const uint64_t dBd = umma::make_sdesc(umma::smem_u32(sW), 16, 512, umma::SWZ_64B);
+        umma::mbar_wait(&w_full[stage], ph);
+        umma::mbar_wait_cluster(&w_full_peer[stage], ph);
+        umma::tc_fence_after();
+        if (umma::elect_one()) {
+            const uint64_t db = dBd + (uint64_t)((stage * kSlot) >> 4);
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) umma::mma_bf16_2cta(d_base, dAd + ks * 2, db + ks * 2, idesc, 1u);
+            umma::mma_commit_2cta(&w_empty[stage], 3);
+        }
+        __syncwarp();
+        if (++stage == kNumStages) { stage = 0; ph ^= 1; }
+    }
+    if (umma::elect_one()) umma::mma_commit_2cta(done_bar, 3);
     __syncwarp();
 }
 
