@@ -18,6 +18,7 @@ using namespace sm100;
 namespace {
 
 struct FwdParams {
+    WeightMaps maps;              // tensor maps of the packed weights (CTA-pair kernels)
     int n_layers;
     FwdLayer layers[kMaxLayers];
     const uint8_t* packed;
@@ -161,7 +162,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     if (2 * r + g >= T) continue;
                     const FwdLayer& L = p.layers[l];
                     const int n_dir = L.has_dir ? L.n_halves : 0;
-                    if (CG == 2) produce_stages_2cta(p.packed + L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
+                    if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
                     else produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
                 }
     } else if (warp == 1) {
@@ -172,15 +173,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 for (int g = 0; g < 2; ++g) {
                     if (2 * r + g >= T) continue;
                     const FwdLayer& L = p.layers[l];
-                    if (CG == 2 && rank != 0) {      // partner CTA: only reports its weight halves
-                        forward_stages_2cta(L.n_kchunks + (L.has_dir ? 1 : 0), w_full, w_full_peer, stage, ph);
-                        continue;
-                    }
+                    if (CG == 2 && rank != 0) continue;      // the partner CTA issues no MMAs
                     if (CG == 2) umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
                     else umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
                     umma::tc_fence_after();
                     if (CG == 2)
-                        issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_full_peer,
+                        issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full,
                                         w_empty, L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
                     else
                         issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty,
@@ -414,6 +412,7 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     static const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();
     if (use_pairs && grid >= 2) {
         grid &= ~1;
+        CNB_TRY(make_weight_maps(packed, pl.total_bytes, &fp.maps));
         CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
@@ -496,6 +495,28 @@ size_t cnb_sm100_render_workspace_bytes(const cnb_net_config* cfg, const cnb_ray
 }
 
 namespace sm100 {
+int make_weight_maps(const void* packed, size_t bytes, WeightMaps* out) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* f = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) f = nullptr;
+        return (EncodeFn)f;
+    }();
+    if (!fn) return CNB_E_DEVICE;
+    const cuuint64_t dims[2] = {64, (cuuint64_t)(bytes / 128)};     // rows of 64 bf16 = 128 bytes
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box16[2] = {64, 128}, box8[2] = {64, 64};
+    if (fn(&out->m16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(packed), dims, strides, box16, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return CNB_E_INVALID;
+    if (fn(&out->m8, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(packed), dims, strides, box8, estr,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return CNB_E_INVALID;
+    return CNB_OK;
+}
 // K1 over rays [ray_begin, ray_begin + ray_count) of the batch; outputs indexed by global ray,
 // the optional per-sample spill by launch-relative row.
 int launch_render_rays(const cnb_net_config* cfg, const float* const* P, const void* packed, const Plan& pl,

@@ -3,6 +3,7 @@
 #pragma once
 #include "render_sm100.cuh"
 #include "mlp_fp32.cuh"
+#include <cuda.h>
 #include "umma.cuh"
 #include <type_traits>
 
@@ -234,45 +235,41 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t d_base, uin
 
 // ---- CTA-pair (cta_group::2) versions: each CTA streams HALF of every weight chunk (its 128 of the 256
 // output columns, or 64 of 128), the leader issues M = 256 MMAs covering one tile of each CTA ------------
+// Tensor maps over the packed weight buffer viewed as rows of 128 bytes: boxes of 128 rows (16 KB) / 64 rows (8 KB).
+struct alignas(64) WeightMaps { CUtensorMap m16, m8; };
+
 // stages of one GEMM for CTA `rank`: chunk c -> image (c * n_halves + rank) [n_halves == 2], or the
 // rank-th 8 KB of image c [n_halves == 1]; the PE(viewdir) chunk -> image (n_main + rank), 8 KB.
-__device__ __forceinline__ void produce_stages_2cta(const uint8_t* __restrict__ src, int n_kchunks, int n_halves, int has_dir,
-                                                    uint32_t rank, uint8_t* sW, uint64_t* w_full, uint64_t* w_empty,
-                                                    int& stage, uint32_t& ph) {
+// Every load completes on the LEADER's barrier; the leader arms it with the bytes of both CTAs.
+__device__ __forceinline__ void produce_stages_2cta(const WeightMaps* maps, uint32_t w_off, int n_kchunks, int n_halves,
+                                                    int has_dir, uint32_t rank, uint8_t* sW, uint64_t* w_full,
+                                                    uint64_t* w_empty, int& stage, uint32_t& ph) {
     const int n = n_kchunks + (has_dir ? 1 : 0);
+    const uint32_t full0 = umma::mapa(umma::smem_u32(&w_full[0]), 0);
     for (int c = 0; c < n; ++c) {
         umma::mbar_wait(&w_empty[stage], ph ^ 1);
         if (umma::elect_one()) {
             const bool dir = c >= n_kchunks;
-            const uint32_t bytes = (dir || n_halves == 1) ? kSlot / 2 : kSlot;
-            const uint8_t* s = dir ? src + (size_t)(n_kchunks * n_halves + rank) * kSlot
-                                   : (n_halves == 2 ? src + (size_t)(c * 2 + rank) * kSlot : src + (size_t)c * kSlot + rank * (kSlot / 2));
-            umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
-            umma::bulk_g2s(sW + stage * kSlot, s, bytes, &w_full[stage]);
+            const bool small = dir || n_halves == 1;
+            const uint32_t off = dir ? w_off + (uint32_t)(n_kchunks * n_halves + rank) * kSlot
+                                     : (n_halves == 2 ? w_off + (uint32_t)(c * 2 + rank) * kSlot : w_off + (uint32_t)c * kSlot + rank * (kSlot / 2));
+            if (rank == 0) umma::mbar_arrive_expect_tx(&w_full[stage], small ? kSlot : 2 * kSlot);
+            umma::tma_load_2d_pair(sW + stage * kSlot, small ? (const void*)&maps->m8 : (const void*)&maps->m16, 0, (int)(off >> 7),
+                                   full0 + stage * 8);
         }
-        __syncwarp();
-        if (++stage == kNumStages) { stage = 0; ph ^= 1; }
-    }
-}
-// peer CTA: tell the leader when this CTA's half of each stage has landed
-__device__ __forceinline__ void forward_stages_2cta(int n_stages, uint64_t* w_full, uint64_t* w_full_peer, int& stage, uint32_t& ph) {
-    for (int c = 0; c < n_stages; ++c) {
-        umma::mbar_wait(&w_full[stage], ph);
-        if (umma::elect_one()) umma::mbar_arrive_cluster(umma::mapa(umma::smem_u32(&w_full_peer[stage]), 0));
         __syncwarp();
         if (++stage == kNumStages) { stage = 0; ph ^= 1; }
     }
 }
 // leader CTA: issue one GEMM for the pair's two tiles (M = 256)
 __device__ __forceinline__ void issue_gemm_2cta(uint32_t a_base, uint32_t d_base, uint8_t* sW, uint64_t* w_full,
-                                                uint64_t* w_full_peer, uint64_t* w_empty, int n_kchunks, int n_halves,
+                                                uint64_t* w_empty, int n_kchunks, int n_halves,
                                                 int has_dir, int& stage, uint32_t& ph, uint64_t* done_bar) {
     const uint64_t dA = umma::make_sdesc(a_base, 16, 1024, umma::SWZ_128B);
     const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
     const uint32_t idesc = umma::make_idesc(256, n_halves * 128, 0, 0);
     for (int c = 0; c < n_kchunks; ++c) {
-        umma::mbar_wait(&w_full[stage], ph);
-        umma::mbar_wait_cluster(&w_full_peer[stage], ph);
+        umma::mbar_wait_cluster(&w_full[stage], ph);
         umma::tc_fence_after();
         if (umma::elect_one()) {
             const uint64_t da = dA + (uint64_t)((c * kABlock) >> 4);
@@ -287,8 +284,7 @@ __device__ __forceinline__ void issue_gemm_2cta(uint32_t a_base, uint32_t d_base
     if (has_dir) {
         const uint64_t dAd = umma::make_sdesc(a_base + 4 * kABlock, 16, 512, umma::SWZ_64B);
         const uint64_t dBd = umma::make_sdesc(umma::smem_u32(sW), 16, 512, umma::SWZ_64B);
-        umma::mbar_wait(&w_full[stage], ph);
-        umma::mbar_wait_cluster(&w_full_peer[stage], ph);
+        umma::mbar_wait_cluster(&w_full[stage], ph);
         umma::tc_fence_after();
         if (umma::elect_one()) {
             const uint64_t db = dBd + (uint64_t)((stage * kSlot) >> 4);
@@ -416,6 +412,9 @@ inline size_t carve_fwd(const cnb_net_config* c, int n_codes, int64_t spill_samp
 // z_j = ReLU(latent layer_j(code)) and the folded per-code biases (defined in render_sm100.cu).
 int latent_and_fold(const cnb_net_config* c, const float* const* P, const float* shape_codes, const float* tex_codes,
                     int n_codes, FwdWorkspace& w, cudaStream_t st);
+
+// Tensor maps of the packed weight buffer (defined in render_sm100.cu); CNB_OK or a status.
+int make_weight_maps(const void* packed, size_t bytes, WeightMaps* out);
 
 // K1 over a ray sub-range (defined in render_sm100.cu).
 int launch_render_rays(const cnb_net_config* cfg, const float* const* P, const void* packed, const Plan& pl,

@@ -179,6 +179,14 @@ __device__ __forceinline__ void mma_commit_2cta(uint64_t* bar, uint16_t mask) {
                  ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
+// Tensor-map TMA load of one 2-D box into THIS CTA's shared memory, completing on an mbarrier of the pair's
+// leader CTA (`leader_bar` = mapa(bar, 0)): the cta_group::2 form that feeds 2-CTA MMAs without a forwarding hop.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
 //   bits [4,6) D format (1 = f32), [7,10) A format (1 = bf16), [10,13) B format (1 = bf16),
