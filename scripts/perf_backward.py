@@ -1,5 +1,5 @@
 import sys, time, torch, numpy as np, ctypes
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import codenerf_b200 as cn
 from codenerf_b200 import synthetic as syn, ops, _lib
 from tests import gpu_util as U

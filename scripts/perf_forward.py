@@ -1,10 +1,10 @@
 import sys, time, torch, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
 import codenerf_b200 as cn
 from codenerf_b200 import synthetic as syn
 from tests import gpu_util as U
 model, flat = U.make_model("bf16")
-for N, n_seg in ((64, 32),):
+for N, n_seg in ((64, 32), (64, 64), (96, 32)):
     R = 2048
     c2ws = np.stack([syn.look_at_pose(700 + g, 1.3) for g in range(n_seg)])
     zs = np.stack([np.linspace(0.8, 1.8, N).astype(np.float32) for g in range(n_seg)])
