@@ -49,6 +49,7 @@ struct BwdParams {
     uint32_t* mask_scratch;         // [grid][2][n_layers][8][128]
     float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l
     int stash;                      // 1: stream operand tiles + dspre to HBM (training)
+    uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
     uint8_t *stashA, *stashD;
     float* dspre;                   // [S] d(loss)/d(sigma pre-activation)
     // fused compositing (+ loss) when every tile holds whole rays (128 % N == 0): the seeds are made in-kernel
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
                     umma::bulk_commit();
                 }
-                if (out_layer >= 0 && lane < blocks * 8) {
+                if (out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
                     const int blk = lane >> 3, chunk = lane & 7;
                     float acc[8];
 #pragma unroll
@@ -521,7 +522,7 @@ struct WgProblem {
     uint8_t m_blocks;     // dY width / 64 (2 or 4)
     uint8_t n_blocks;     // input width / 64 (1 or 4)
     uint8_t is_dir;       // input is the [128 x 32] PE(viewdir) block (64-B swizzle)
-    uint8_t pad;
+    uint8_t layer;        // fwd layer of dY_l: slot of its column sums (bias / latent-code gradients); 0xff: none
     int32_t splits;       // work items this problem is cut into (along rows)
     int32_t item0;        // index of its first work item
 };
@@ -532,6 +533,9 @@ struct WgParams {
     uint32_t a_tile_bytes, d_tile_bytes;
     int64_t n_tiles;
     float* dP;
+    float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l (reduced here from the staged tiles)
+    int n_layers, n_codes;
+    int64_t rows_per_code, row_offset;
 };
 constexpr int kWgStage = 65536;      // 64 rows: dY half-blocks [0, 32 KB) + input half-blocks [32 KB, 64 KB)
 constexpr int kWgStages = 3;
@@ -558,7 +562,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWgStages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+        for (int i = 0; i < kWgStages; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1 + 4); }   // MMA commit + 4 reducer warps
         umma::mbar_init(acc_done, 1); umma::mbar_init(acc_free, 4);
         umma::fence_mbar_init();
     }
@@ -631,11 +635,62 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const int wq = warp - 2;                 // reducer index 0..3: owns dY half-block wq of every stage
+        const int chunk = lane & 7, rg = lane >> 3;
         uint32_t it = 0;
+        int stage = 0; uint32_t ph = 0;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
             int pi; int64_t hb, he;
             wg_item(p, item, pi, hb, he);
             const WgProblem& P = p.prob[pi];
+            // ---- column sums of dY_l from the staged half-tiles (bias and latent-code gradients) ----
+            const bool reduce = P.layer != 0xff && wq < P.m_blocks;
+            float cs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+            int64_t cur_code = -1;
+            auto flush_cs = [&]() {
+                if (cur_code < 0) return;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 8);
+                    cs[i] += __shfl_xor_sync(0xffffffffu, cs[i], 16);
+                }
+                if (rg == 0) {
+                    float* out = p.colsum + ((size_t)cur_code * p.n_layers + P.layer) * kW + wq * 64 + chunk * 8;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) atomicAdd(out + i, cs[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+            };
+            for (int64_t h = hb; h < he; ++h) {
+                umma::mbar_wait(&full[stage], ph);
+                if (reduce) {
+                    int64_t code = 0;
+                    if (p.n_codes > 1) { code = (p.row_offset + (h >> 1) * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+                    if (code != cur_code) { flush_cs(); cur_code = code; }
+                    const uint8_t* base = smem + stage * kWgStage + wq * 8192;
+                    uint4 w[16];                  // load first, release the stage, then add
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const int rr = rg * 16 + i;
+                        w[i] = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                    }
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&empty[stage]);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        cs[0] += bf_lo(w[i].x); cs[1] += bf_hi(w[i].x); cs[2] += bf_lo(w[i].y); cs[3] += bf_hi(w[i].y);
+                        cs[4] += bf_lo(w[i].z); cs[5] += bf_hi(w[i].z); cs[6] += bf_lo(w[i].w); cs[7] += bf_hi(w[i].w);
+                    }
+                } else {
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&empty[stage]);
+                }
+                if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+            }
+            if (reduce) flush_cs();
             umma::mbar_wait(acc_done, it & 1u);
             umma::tc_fence_after();
             const int ncols = P.is_dir ? 32 : P.n_blocks * 64;
@@ -880,6 +935,11 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
     bp.mask_scratch = w.masks; bp.colsum = w.colsum;
     bp.stash = d_params ? 1 : 0; bp.stashA = w.stashA; bp.stashD = w.stashD; bp.dspre = w.dspre;
+    // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux
+    // warps of K2 do it, and only for the folded layers (the latent-code gradients need nothing else)
+    bp.colsum_layers = 0u;
+    if (!d_params)
+        for (int l = 0; l < nl; ++l) if (pl.fwd[l].folded >= 0) bp.colsum_layers |= 1u << l;
     bp.b_rgb2 = P[L.i_rgb2 + 1];
     if (fuse) {
         bp.fuse_comp = fuse->kind; bp.white_bg = fuse->white_bg; bp.n_rays_total = fuse->n_rays_total;
@@ -911,6 +971,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         WgProblem q = {};
         q.d_off = sl.d_slot[lay]; q.a_off = a_off; q.w_off = w_off; q.ld = ld; q.col0 = col0; q.n_valid = n_valid;
         q.m_blocks = (uint8_t)(pl.fwd[lay].n_halves * 2); q.n_blocks = (uint8_t)n_blocks; q.is_dir = (uint8_t)is_dir;
+        q.layer = is_dir ? (uint8_t)0xff : (uint8_t)lay;      // each dY_l is reduced exactly once
         wp.prob[np++] = q;
     };
     {
@@ -938,6 +999,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     wp.n_problems = np; wp.n_items = items;
     wp.stashA = w.stashA; wp.stashD = w.stashD; wp.a_tile_bytes = sl.a_tile_bytes; wp.d_tile_bytes = sl.d_tile_bytes;
     wp.n_tiles = tiles; wp.dP = d_params;
+    wp.colsum = w.colsum; wp.n_layers = nl; wp.n_codes = n_codes; wp.rows_per_code = rows_per_code; wp.row_offset = row_offset;
     const size_t wsmem = 1024 + (size_t)kWgStages * kWgStage + 256;
     CNB_CUDA_TRY(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     const int wgrid = items < sms ? items : sms;
