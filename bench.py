@@ -218,8 +218,6 @@ def run_ours(args):
         for _ in range(warmup):
             fn()
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
         sampler = None
         if sample_clocks and rank == 0:
             sampler = ClockSampler(local)
@@ -228,6 +226,9 @@ def run_ours(args):
         L.cnb_profile_enable(1)
         l0 = L.cnb_launch_count()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()              # every rank enters the timed region together
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
@@ -250,9 +251,17 @@ def run_ours(args):
         clocks = sampler.finish() if sampler else None
         return float(ms.item()) / steps, launches, kt, clocks
 
+    d_seed = torch.from_numpy(tgt).to(dev) * 1e-4       # any per-ray d_rgb: the latent-fit leg times the kernels only
+
+    def latent_only():
+        # optimize.py's step body: gradients for the codes only (no weight-gradient pass, no HBM stash)
+        rb = make_bundle(d_c2w, d_z).args(d_sc, d_tc)
+        return ops.render_backward(model._cfg, params, packed, rb, prec, d_seed, None, False)
+
     ms_step, launches, kt, clocks = timed(lambda: step(d_c2w, d_z, d_tgt), args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _, _, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     ms_fwd, _, kt_f, _ = timed(fwd_only, args.steps, 2)
+    ms_lat, _, _, _ = timed(latent_only, args.steps, 2)
     timeouts = L.cnb_debug_pipeline_timeouts()
 
     if rank == 0:
@@ -271,8 +280,14 @@ def run_ours(args):
             flop_per_sample = {"fwd": FLOP_FWD, "bwd": FLOP_FWD + FLOP_DGRAD, "wgrad": FLOP_FWD}[dom]
             achieved = samples / launches_per_step * flop_per_sample / (per_launch_ms * 1e-3) / 1e12
             peak = peaks["bf16_tflops_sustained"] or peaks["bf16_tflops"]
+            traffic = None          # dram bytes per launch of that kernel from the committed ncu --set full capture
+            tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+            if os.path.exists(tpath):
+                t = json.load(open(tpath))
+                if t.get("objects") == n_obj and dom in t.get("dram_bytes_per_launch", {}):
+                    traffic = t["dram_bytes_per_launch"][dom]
             roof = {"bound": "tensor", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"] + " sustained",
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": peaks["source"] + " sustained",
                     "ms_per_launch": per_launch_ms, "share_of_step": kmean[dom] / ms_step}
         fwd_tflops = samples * FLOP_FWD / (ms_fwd * 1e-3) / 1e12
         line = {
@@ -295,6 +310,8 @@ def run_ours(args):
             "train_frac_of_bf16_peak": value * N_SAMPLES * FLOP_TRAIN / 1e12 / (peaks["bf16_tflops"] * world),
             "fwd_rays_per_s": total_rays / (ms_fwd * 1e-3),
             "fwd_tflops": fwd_tflops, "fwd_frac_of_bf16_peak": fwd_tflops / peaks["bf16_tflops"],
+            "latent_fit_rays_per_s": total_rays / (ms_lat * 1e-3),
+            "latent_fit_frac_of_bf16_peak": samples * (FLOP_FWD + FLOP_DGRAD) / (ms_lat * 1e-3) / 1e12 / peaks["bf16_tflops"],
             "kernel_ms_per_step": kmean,
             "pipeline_timeouts": int(timeouts),
         }

@@ -14,6 +14,7 @@
 //
 // Reference semantics: autograd of src/model.py:36-53 (what loss.backward() does in
 // src/trainer.py:82 and src/optimizer.py:92).
+#include <cstdlib>
 #include "sm100_common.cuh"
 
 using namespace sm100;
@@ -984,14 +985,15 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         for (int j = 0; j < c->texture_blocks; ++j, ++l) add(l, L.t_w[j], kW, 0, kW, 4, sl.a_slot[l], 0);
         add(l, L.rgb0_w, kW, 0, kW, 4, sl.a_slot[l], 0);
     }
-    // split rows so that ~2 work items per SM exist, each spanning >= 8 half-tiles
+    // split rows into ~k3_items_per_sm work items per SM (each ends with an atomic flush of its dW tile), >= 8 half-tiles each
+    static const double k3_items_per_sm = [] { const char* e = getenv("CNB_K3_ITEMS_PER_SM"); return e ? atof(e) : 2.0; }();
     double total_cost = 0;
-    for (int i = 0; i < np; ++i) total_cost += (double)wp.prob[i].m_blocks * (wp.prob[i].is_dir ? 1 : wp.prob[i].n_blocks);
+    for (int i = 0; i < np; ++i) total_cost += (double)wp.prob[i].m_blocks + (wp.prob[i].is_dir ? 0.5 : wp.prob[i].n_blocks);   // HBM bytes per half-tile
     const int64_t H = tiles * 2;
     int items = 0;
     for (int i = 0; i < np; ++i) {
-        const double cost = (double)wp.prob[i].m_blocks * (wp.prob[i].is_dir ? 1 : wp.prob[i].n_blocks);
-        int64_t sp = (int64_t)(2.0 * sms * cost / total_cost + 0.5);
+        const double cost = (double)wp.prob[i].m_blocks + (wp.prob[i].is_dir ? 0.5 : wp.prob[i].n_blocks);
+        int64_t sp = (int64_t)(k3_items_per_sm * sms * cost / total_cost + 0.5);
         if (sp > H / 8) sp = H / 8;
         if (sp < 1) sp = 1;
         wp.prob[i].splits = (int32_t)sp; wp.prob[i].item0 = items; items += (int)sp;
