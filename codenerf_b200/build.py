@@ -36,6 +36,7 @@ def build(force=False, verbose=False):
         o = os.path.join(HERE, "..", "build", s.replace(".cu", ".o"))
         cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, s), "-o", o]
+        cmd[1:1] = os.environ.get("CNB_NVCC_EXTRA", "").split()      # e.g. -DCNB_TRACE (debug builds)
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False

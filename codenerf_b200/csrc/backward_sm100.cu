@@ -19,6 +19,14 @@
 
 using namespace sm100;
 
+#ifdef CNB_TRACE
+extern "C" int cnb_debug_trace_bwd(unsigned long long* out32, int reset) {
+    if (out32 && cudaMemcpyFromSymbol(out32, sm100::g_trace, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[32] = {}; if (cudaMemcpyToSymbol(sm100::g_trace, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif
+
 namespace {
 
 constexpr int kBwdThreads = 384;   // warp 0 producer, 1 MMA, 2-5 group X, 6-9 group Y, 10/11 aux X/Y
@@ -186,8 +194,8 @@ __device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const u
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = pk2(rr[j8 * 8 + 2 * i], rr[j8 * 8 + 2 * i + 1]);
         if (ADD_SIGMA) {
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_sigma + col));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_sigma + col + 4));
+            const float4 w0 = ld_vec4<true>(w_sigma + col);      // shared-memory copy of the sigma-head weights
+            const float4 w1 = ld_vec4<true>(w_sigma + col + 4);
             v[0] = ffma2(dsp2, pk2f(w0.x, w0.y), v[0]); v[1] = ffma2(dsp2, pk2f(w0.z, w0.w), v[1]);
             v[2] = ffma2(dsp2, pk2f(w1.x, w1.y), v[2]); v[3] = ffma2(dsp2, pk2f(w1.z, w1.w), v[3]);
         }
@@ -228,6 +236,9 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
     pair(std::integral_constant<int, 6>{});
 }
 
+// MC > 1: clusters of MC CTAs share one multicast weight stream (see produce_stages); every CTA of a cluster runs
+// the same number of tile slots, the surplus ones as phantom tiles (all rows invalid, nothing written).
+template <int MC>
 __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constant__ BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -243,6 +254,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     uint32_t* tmem_slot = (uint32_t*)(buf_free + 2);
     float4* sSamp = (float4*)(tmem_slot + 4);      // [2][128] per-sample (sigma, r, g, b) of the group's tile
     float4* sSeed = sSamp + 2 * kTileRows;         // [2][128] per-sample (d sigma, d r, d g, d b)
+    float* sBias = (float*)(sSeed + 2 * kTileRows);  // [2 groups][2 buffers][256] bias row of the layer being drained
+    float* sWsig = sBias + 4 * kW;                  // [256] sigma-head weights
+    float* sWrgb = sWsig + kW;                      // [3][128] rgb.2 weights
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = p.n_layers, ns = p.n_steps;
@@ -251,11 +265,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
     const int64_t tbase = tiles / gridDim.x, trem = tiles % gridDim.x;
     const int64_t tile0 = (int64_t)blockIdx.x * tbase + min((int64_t)blockIdx.x, trem);
-    const int T = (int)(tbase + ((int64_t)blockIdx.x < trem ? 1 : 0));
+    const int T_own = (int)(tbase + ((int64_t)blockIdx.x < trem ? 1 : 0));
+    const uint32_t rank = MC > 1 ? umma::cluster_ctarank() : 0u;
+    const int T = MC > 1 ? (int)(tbase + ((int64_t)(blockIdx.x - rank) < trem ? 1 : 0)) : T_own;   // cluster-uniform
     const int rounds = (T + 1) >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], MC); }
         for (int g = 0; g < 2; ++g) {
             umma::mbar_init(&a_ready[g], 4); umma::mbar_init(&acc_full[g], 1);
             umma::mbar_init(&aux_ready[g], 4); umma::mbar_init(&buf_free[g], 1);
@@ -263,14 +279,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         umma::fence_mbar_init();
     }
     if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
+    for (int i = threadIdx.x; i < kW; i += kBwdThreads) sWsig[i] = __ldg(p.w_sigma + i);
+    for (int i = threadIdx.x; i < 3 * (kW / 2); i += kBwdThreads) sWrgb[i] = __ldg(p.w_rgb2 + i);
     umma::tc_fence_before();
-    __syncthreads();
+    if (MC > 1) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    const float* wsig_s = smem_fptr(sWsig);
+    const float* wrgb_s = smem_fptr(sWrgb);
 
     if (warp == 0) {
         // ===== weight producer =====
         int stage = 0; uint32_t ph = 0;
+        const uint64_t pol_w = p.stash ? umma::l2_policy_evict_last() : 0ull;   // the stash stream must not evict the weights
         for (int r = 0; r < rounds; ++r)
             for (int op = 0; op < n_ops; ++op)
                 for (int g = 0; g < 2; ++g) {
@@ -278,15 +299,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     if (op < nl) {
                         const FwdLayer& L = p.layers[op];
                         const int n_dir = L.has_dir ? L.n_halves : 0;
-                        produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
+                        produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                     } else {
                         const BwdStep& B = p.steps[op - nl + 1];
-                        produce_stages(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph);
+                        produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                     }
                 }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int stage = 0; uint32_t ph = 0;
+        CNB_TR_DECL(tr_wa); CNB_TR_DECL(tr_ww); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
         for (int r = 0; r < rounds; ++r)
             for (int op = 0; op < n_ops; ++op)
                 for (int g = 0; g < 2; ++g) {
@@ -294,11 +317,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     int n_kchunks, n_halves, has_dir;
                     if (op < nl) { n_kchunks = p.layers[op].n_kchunks; n_halves = p.layers[op].n_halves; has_dir = p.layers[op].has_dir; }
                     else { n_kchunks = p.steps[op - nl + 1].n_kchunks; n_halves = 2; has_dir = 0; }
-                    umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u);
+                    CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
                     umma::tc_fence_after();
-                    issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
-                               n_halves, has_dir, stage, ph, &acc_full[g]);
+                    issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                                   n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
                 }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        CNB_TR_FLUSH(0, tr_wa); CNB_TR_FLUSH(1, tr_ww); CNB_TR_FLUSH(2, tr_tot);
     } else if (warp >= 10) {
         // ===== auxiliary warps: operand stash (TMA bulk stores) and column sums of every dY =====
         const int g = warp - 10;
@@ -306,15 +331,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         uint32_t ap = 0;
         const uint64_t pol_stream = umma::l2_policy_evict_first();   // the stash is written once and read by a later kernel
         const int n_phases = nl + 1 + ns;
+        CNB_TR_DECL(tr_wx); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
         for (int r = 0; r < rounds; ++r) {
             const int t = 2 * r + g;
             if (t >= T) break;
+            const bool phantom = t >= T_own;
+            const bool stash = p.stash && !phantom;
             const int64_t tile = tile0 + t;
             int64_t code = 0;
             if (p.n_codes > 1) { code = (p.row_offset + tile * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
             for (int phs = 0; phs < n_phases; ++phs) {
                 if (phs == nl && !p.stash) continue;      // the rgb.2 input is only written for the stash
-                umma::mbar_wait(&aux_ready[g], ap & 1u); ++ap;
+                CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
                 int blocks = 0, out_layer = -1;
                 uint8_t* dst = nullptr;
                 if (phs == 0) { blocks = 1; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[0]; }
@@ -325,13 +354,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     blocks = B.out_blocks; out_layer = B.out_layer;
                     dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
                 }
-                if (p.stash && lane == 0) {
+                if (stash && lane == 0) {
                     umma::bulk_s2g_hint(dst, sA, (uint32_t)blocks * kABlock, pol_stream);
                     if (phs == 0)
                         umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
                     umma::bulk_commit();
                 }
-                if (out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
+                if (!phantom && out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
                     const int blk = lane >> 3, chunk = lane & 7;
                     float acc[8];
 #pragma unroll
@@ -347,12 +376,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
                 }
-                if (p.stash && lane == 0) umma::bulk_wait_read_all();
+                if (stash && lane == 0) umma::bulk_wait_read_all();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&buf_free[g]);
             }
         }
         if (p.stash && lane == 0) umma::bulk_wait_all();
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        if (g == 0) { CNB_TR_FLUSH(3, tr_wx); CNB_TR_FLUSH(4, tr_tot); }
     } else {
         // ===== compute groups =====
         const int g = (warp - 2) >> 2;
@@ -368,8 +399,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
         uint32_t opc = 0;     // accumulator phases consumed
         uint32_t* mscr = p.mask_scratch + ((size_t)(blockIdx.x * 2 + g) * nl) * 8 * kTileRows + row;
+        const int tg = ((warp - 2) & 3) * 32 + lane;     // thread index inside the group
+        float* sB = sBias + g * 2 * kW;
+        uint32_t bsel = 0;                               // staging buffer of the next layer (alternates)
 
-        auto wait_buf_free = [&]() { if (wp > 0) umma::mbar_wait(&buf_free[g], (wp - 1) & 1u); };
+        CNB_TR_DECL(tr_wbuf); CNB_TR_DECL(tr_wacc_f); CNB_TR_DECL(tr_epi_f); CNB_TR_DECL(tr_mid); CNB_TR_DECL(tr_wacc_b);
+        CNB_TR_DECL(tr_epi_b); CNB_TR_DECL(tr_enc); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
+        auto wait_buf_free = [&]() { if (wp > 0) CNB_TR(tr_wbuf, umma::mbar_wait(&buf_free[g], (wp - 1) & 1u)); };
         auto publish = [&](bool to_mma) {
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
@@ -381,8 +418,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         for (int r = 0; r < rounds; ++r) {
             const int t = 2 * r + g;
             if (t >= T) break;
+            const bool phantom = t >= T_own;
+            const long long tr_e0 = CNB_TR_NOW();
             const int64_t lrow = (tile0 + t) * kTileRows + row;      // launch-relative row
-            const bool valid = lrow < p.S;
+            const bool valid = !phantom && lrow < p.S;
             const int64_t grow = p.row_offset + lrow;                // global row
             float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
             float ds = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
@@ -412,28 +451,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             wait_buf_free();
             encode_row(pos, dir, valid, sA, sA + 4 * kABlock, row);
             publish(true);
+            tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
             // ---- forward chain (recompute) ----
             HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, pol_keep};
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
-                umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
+                const float* bias_g = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
+                float2 bias2 = make_float2(0.f, 0.f);
+                if (2 * tg < L.n_halves * 128) bias2 = __ldg(reinterpret_cast<const float2*>(bias_g) + tg);   // in flight during the wait
+                CNB_TR(tr_wacc_f, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                const long long tr_p0 = CNB_TR_NOW();
                 umma::tc_fence_after();
-                const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
                 const bool last = (l + 1 == nl);
                 const bool store = !last || p.stash;
                 if (store) wait_buf_free();
+                // the layer's bias row goes through shared memory: 2 floats per thread, then LDS broadcasts
+                float* sb = sB + bsel * kW; bsel ^= 1u;
+                if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
+                umma::named_bar_sync(1 + g, 128);
+                const float* bias = smem_fptr(sb);
                 uint32_t* ml = mscr + (size_t)l * 8 * kTileRows;
-                if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
-                else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                 else if (p.fuse_comp) {
-                    if (store) fwd_epilogue_layer<4, 2, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
-                    else fwd_epilogue_layer<4, 2, false, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                    if (store) fwd_epilogue_layer<4, 2, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                    else fwd_epilogue_layer<4, 2, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                 }
-                else if (store) fwd_epilogue_layer<4, 0, true, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
-                else fwd_epilogue_layer<4, 0, false, true>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, ml);
+                else if (store) fwd_epilogue_layer<4, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                else fwd_epilogue_layer<4, 0, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                 if (store) publish(!last);
+                tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
             }
+            const long long tr_m0 = CNB_TR_NOW();
             float sig_pre;
             { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
             const float x = sig_pre + __ldg(p.b_sigma);
@@ -448,7 +498,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 samp[row] = make_float4(cnb_softplus(x), cr, cg, cb);
                 umma::named_bar_sync(1 + g, 128);
                 const int rays_in_tile = kTileRows / N;
-                const int64_t ray_base = (p.row_offset + (tile0 + t) * kTileRows) / N;
+                const int64_t ray_base = phantom ? p.n_rays_total : (p.row_offset + (tile0 + t) * kTileRows) / N;
                 for (int k = (warp - 2) & 3; k < rays_in_tile; k += 4)
                     composite_fwd_bwd(p, samp + k * N, seed + k * N, ray_base + k, lane);
                 umma::named_bar_sync(1 + g, 128);
@@ -474,9 +524,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     uint32_t w[4];
 #pragma unroll
                     for (int hh = 0; hh < 2; ++hh) {
-                        const float4 w0 = __ldg(reinterpret_cast<const float4*>(p.w_rgb2 + col + hh * 4));
-                        const float4 w1 = __ldg(reinterpret_cast<const float4*>(p.w_rgb2 + (kW / 2) + col + hh * 4));
-                        const float4 w2 = __ldg(reinterpret_cast<const float4*>(p.w_rgb2 + kW + col + hh * 4));
+                        const float4 w0 = ld_vec4<true>(wrgb_s + col + hh * 4);
+                        const float4 w1 = ld_vec4<true>(wrgb_s + (kW / 2) + col + hh * 4);
+                        const float4 w2 = ld_vec4<true>(wrgb_s + kW + col + hh * 4);
                         uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
                         uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
                         float f0, f1, f2, f3; unpk2(v0, f0, f1); unpk2(v1, f2, f3);
@@ -490,24 +540,32 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 }
             }
             publish(ns > 1);
+            tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
 
             // ---- input-gradient chain ----
             const uint64_t dsp2 = pk2f(dspre, dspre);
             for (int s = 1; s < ns; ++s) {
                 const BwdStep& B = p.steps[s];
-                umma::mbar_wait(&acc_full[g], opc & 1u); ++opc;
+                CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                const long long tr_b0 = CNB_TR_NOW();
                 umma::tc_fence_after();
                 wait_buf_free();
                 const uint32_t* ml = mscr + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
-                if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, p.w_sigma, pol_keep);
-                else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, p.w_sigma, pol_keep);
-                else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, p.w_sigma, pol_keep);
+                if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
+                else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
+                else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                 publish(s + 1 < ns);
+                tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
             }
+        }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        if (warp == 2) {
+            CNB_TR_FLUSH(5, tr_wbuf); CNB_TR_FLUSH(6, tr_wacc_f); CNB_TR_FLUSH(7, tr_epi_f); CNB_TR_FLUSH(8, tr_mid);
+            CNB_TR_FLUSH(9, tr_wacc_b); CNB_TR_FLUSH(10, tr_epi_b); CNB_TR_FLUSH(11, tr_enc); CNB_TR_FLUSH(12, tr_tot);
         }
     }
     umma::tc_fence_before();
-    __syncthreads();
+    if (MC > 1) umma::cluster_sync_all(); else __syncthreads();
     if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
@@ -956,12 +1014,24 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     const int sms = num_sms();
     const int64_t tiles = (S + kTileRows - 1) / kTileRows;
     const int64_t units = (tiles + 1) / 2;
-    const int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256 + 4 * kTileRows * sizeof(float4);
-    CNB_CUDA_TRY(cudaFuncSetAttribute(k_mlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
+    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256 + 4 * kTileRows * sizeof(float4) +
+                        sizeof(float) * (4 * kW + kW + 3 * (kW / 2));
+    const int mc = grid == sms ? weight_multicast() : 1;
+    void (*kern)(const BwdParams) = mc == 4 ? k_mlp_bwd<4> : mc == 2 ? k_mlp_bwd<2> : k_mlp_bwd<1>;
+    CNB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = mc; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = mc > 1 ? 1 : 0;
+    if (mc > 1) CNB_TRY(cluster_grid(kern, &cfg, mc, &grid));
+    cfg.gridDim = dim3(grid);
     cnb_prof_begin(CNB_K_BWD, st);
-    k_mlp_bwd<<<grid, kBwdThreads, smem, st>>>(bp);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, kern, bp);
     cnb_prof_end(CNB_K_BWD, st);
+    if (le != cudaSuccess) return (int)le;
     CNB_LAUNCH_CHECK();
     if (!d_params) return CNB_OK;
 

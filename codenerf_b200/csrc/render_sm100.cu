@@ -15,6 +15,14 @@
 
 using namespace sm100;
 
+#ifdef CNB_TRACE
+extern "C" int cnb_debug_trace(unsigned long long* out32, int reset) {
+    if (out32 && cudaMemcpyFromSymbol(out32, sm100::g_trace, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[32] = {}; if (cudaMemcpyToSymbol(sm100::g_trace, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
+#endif
+
 namespace {
 
 struct FwdParams {
@@ -93,8 +101,12 @@ __device__ __forceinline__ void composite_ray(const FwdParams& p, const float4* 
 
 // CG = 1: one CTA per SM, M = 128 MMAs.  CG = 2: CTA pairs (cluster of 2), tcgen05 cta_group::2 with M = 256:
 // each CTA streams half of every weight chunk, halving L2 and shared-memory operand traffic per row.
-template <int CG>
+// MC > 1 (with CG = 1): clusters of MC CTAs with independent M = 128 MMAs whose weight stream is multicast --
+// every stage leaves L2 once per cluster (the weight stream from L2 is what bounds the CG = 1, MC = 1 kernel).
+template <int CG, int MC>
 __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constant__ FwdParams p) {
+    static_assert(CG == 1 || MC == 1, "pairs and multicast clusters are alternatives");
+    constexpr int kCluster = CG * MC;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA0 = smem;
@@ -108,16 +120,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     uint64_t* w_full_peer = acc_full + 2;        // [kNumStages] (leader of a CTA pair): the peer's half has landed
     uint32_t* tmem_slot = (uint32_t*)(w_full_peer + kNumStages);
     volatile int* final_count = (volatile int*)(tmem_slot + 2);
-    const uint32_t rank = CG == 2 ? umma::cluster_ctarank() : 0u;
+    const uint32_t rank = kCluster > 1 ? umma::cluster_ctarank() : 0u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = p.n_layers;
 
     // ---- this CTA's contiguous share of the work -------------------------------------------
     int64_t row0 = 0, nrows = 0, ray0 = 0;
-    int T = 0;                                   // tile slots of this CTA (pair-uniform when CG == 2)
-    for (int who = 0; who < CG; ++who) {         // who == 0: this CTA; who == 1: its pair partner (only its tile count matters)
-        const int64_t b = who == 0 ? (int64_t)blockIdx.x : (int64_t)(blockIdx.x ^ 1u);
+    int T = 0;                                   // tile slots of this CTA (uniform over its cluster)
+    for (int who = 0; who < kCluster; ++who) {   // only the tile count of the other CTAs of the cluster matters
+        const int64_t b = (int64_t)blockIdx.x - rank + who;
         int64_t r0_, n_, ray0_ = 0;
         if (p.mode == 0) {
             const int64_t base = p.n_rays / gridDim.x, rem = p.n_rays % gridDim.x;
@@ -133,13 +145,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             n_ = min(p.S - r0_, nt * kTileRows);
             if (n_ < 0) n_ = 0;
         }
-        if (who == 0) { row0 = r0_; nrows = n_; ray0 = ray0_; }
+        if ((uint32_t)who == rank) { row0 = r0_; nrows = n_; ray0 = ray0_; }
         T = max(T, (int)((n_ + kTileRows - 1) / kTileRows));
     }
     const int rounds = (T + 1) >> 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], MC); }
         for (int i = 0; i < kNumStages; ++i) umma::mbar_init(&w_full_peer[i], 1);
         for (int g = 0; g < 2; ++g) { umma::mbar_init(&a_ready[g], 4 * CG); umma::mbar_init(&acc_full[g], 1); }
         final_count[0] = 0; final_count[1] = 0;
@@ -147,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     }
     if (warp == 1) { if (CG == 2) umma::tmem_alloc2(tmem_slot, 512); else umma::tmem_alloc(tmem_slot, 512); }
     umma::tc_fence_before();
-    if (CG == 2) umma::cluster_sync_all(); else __syncthreads();
+    if (kCluster > 1) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     // a_ready lives in the leader CTA: the partner's compute warps arrive on it remotely
@@ -156,6 +168,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     if (warp == 0) {
         // ===== weight producer: TMA-engine bulk copies of stage images into the ring =====
         int stage = 0; uint32_t ph = 0;
+        CNB_TR_DECL(tr_we); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
         for (int r = 0; r < rounds; ++r)
             for (int l = 0; l < nl; ++l)
                 for (int g = 0; g < 2; ++g) {
@@ -163,27 +177,33 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     const FwdLayer& L = p.layers[l];
                     const int n_dir = L.has_dir ? L.n_halves : 0;
                     if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
-                    else produce_stages(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph);
+                    else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, &tr_we);
                 }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        CNB_TR_FLUSH(0, tr_we); CNB_TR_FLUSH(1, tr_tot);
     } else if (warp == 1) {
         // ===== MMA issuer: one elected thread drives the tensor core for both tiles =====
         int stage = 0; uint32_t ph = 0;
+        CNB_TR_DECL(tr_wa); CNB_TR_DECL(tr_ww); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
         for (int r = 0; r < rounds; ++r)
             for (int l = 0; l < nl; ++l)
                 for (int g = 0; g < 2; ++g) {
                     if (2 * r + g >= T) continue;
                     const FwdLayer& L = p.layers[l];
                     if (CG == 2 && rank != 0) continue;      // the partner CTA issues no MMAs
-                    if (CG == 2) umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
-                    else umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u);
+                    if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * nl + l) & 1u));
+                    else CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], (uint32_t)(r * nl + l) & 1u));
                     umma::tc_fence_after();
                     if (CG == 2)
                         issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full,
-                                        w_empty, L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
+                                        w_empty, L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g], &tr_ww);
                     else
-                        issue_gemm(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty,
-                                   L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g]);
+                        issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty,
+                                       L.n_kchunks, L.n_halves, L.has_dir, stage, ph, &acc_full[g], &tr_ww);
                 }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        CNB_TR_FLUSH(2, tr_wa); CNB_TR_FLUSH(3, tr_ww); CNB_TR_FLUSH(4, tr_tot);
     } else {
         // ===== compute groups: PE, per-layer epilogues (TMEM -> bias/ReLU -> bf16 operand), heads, compositing =====
         const int g = (warp - 2) >> 2;
@@ -196,9 +216,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         uint32_t a8[8];     // shared address of each 16-byte chunk of this row inside K-block 0 (128-B swizzle)
 #pragma unroll
         for (int c = 0; c < 8; ++c) a8[c] = umma::smem_u32(sA + row * 128 + ((c ^ (row & 7)) << 4));
+        CNB_TR_DECL(tr_wacc); CNB_TR_DECL(tr_epi); CNB_TR_DECL(tr_enc); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
         for (int r = 0; r < rounds; ++r) {
             const int t = 2 * r + g;
             if (t >= T) break;
+            const long long tr_e0 = CNB_TR_NOW();
             const int64_t lrow = (int64_t)t * kTileRows + row;
             const bool valid = lrow < nrows;
             const int64_t grow = row0 + lrow;
@@ -230,11 +253,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             umma::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
+            tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
             HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, 0ull};
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
-                umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u);
+                CNB_TR(tr_wacc, umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u));
+                const long long tr_p0 = CNB_TR_NOW();
                 umma::tc_fence_after();
                 const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
                 if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
@@ -246,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     __syncwarp();
                     if (lane == 0) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
                 }
+                tr_epi += (unsigned long long)(CNB_TR_NOW() - tr_p0);
             }
             float sig_pre, cr, cg, cb;
             { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; unpk2(hacc.r2, a0, a1); cr = a0 + a1;
@@ -284,10 +310,390 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             for (int64_t qr = q_first + wi; qr <= q_last; qr += 4)
                 composite_ray(p, sRing, p.ring_cap, qr * N, p.ray_offset + ray0 + qr, lane);
         }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        if (q == 0) { CNB_TR_FLUSH(5 + 4 * g, tr_wacc); CNB_TR_FLUSH(6 + 4 * g, tr_epi); CNB_TR_FLUSH(7 + 4 * g, tr_enc); CNB_TR_FLUSH(8 + 4 * g, tr_tot); }
     }
     umma::tc_fence_before();
-    if (CG == 2) umma::cluster_sync_all(); else __syncthreads();
+    if (kCluster > 1) umma::cluster_sync_all(); else __syncthreads();
     if (warp == 1) { if (CG == 2) umma::tmem_dealloc2(tmem, 512); else umma::tmem_dealloc(tmem, 512); }
+}
+
+// ===========================================================================
+// K1, tensor-memory operand form (default).  What bounds the kernel above is the weight stream: with both
+// operand tiles in shared memory only a 4-slot (64 KB) ring fits, and a slot's round trip (MMA done -> refill
+// from L2 -> MMA) is ~1500 cycles (tests/probe_ts.cu: 3058 cycles per 128x256x256 layer with 4 slots, 2360 with
+// 8).  Here the activations never touch shared memory:
+//   TMEM  [0,128) D0, [128,256) D1 : fp32 accumulators of the two 128-column halves of a layer
+//         [256,384) A_X, [384,512) A_Y : the bf16 operand (K = 256) of tiles X and Y (tcgen05.st, "TS" MMAs)
+//   SMEM  a 9/10-slot weight ring; every stage is used by tile X and, one layer-time later, by tile Y before it
+//         is released (half the L2 -> SM traffic, 2300 cycles of slack per refill); PE blocks of the next tiles.
+// Tensor pipe order per layer: X.h0 -> D0, X.h1 -> D1, Y.h0 -> D0, Y.h1 -> D1.  The eight epilogue warps (two per
+// TMEM lane quarter, 64 columns each) drain a half while the next one is computed: + bias, ReLU, bf16, and the
+// packed result goes back to A_tile once the layer's MMAs have all read it.  Four more warps generate rays /
+// samples / positional encodings two tiles ahead and composite finished rays, so tile boundaries cost nothing.
+constexpr int kTsThreads = 512;      // warp 0 producer, 1 MMA, 2-3 idle, 4-11 epilogue, 12-15 rays + PE + compositing
+constexpr int kTsMaxSlots = 10;
+constexpr uint32_t kColA = 256;
+
+struct TsBars {
+    uint64_t full[kTsMaxSlots], empty[kTsMaxSlots];
+    uint64_t pe_ready[2], xyz_free[2], dir_free[2];   // positional encodings of the tile in slot X / Y
+    uint64_t a_ready[2];                              // A_tile rewritten for the next layer
+    uint64_t d_full[2], d_free[2];                    // accumulator halves
+    uint64_t samp_full[2], samp_free[2];              // per-sample (sigma, rgb) of a finished tile in the sample ring
+    uint32_t tmem_slot, pad;
+};
+
+// 32 accumulator columns -> + bias, heads, [ReLU] bf16 pairs in out[OFF .. OFF + 16).  Pointers are pre-offset to
+// the first of the 32 columns.  KIND: 0 hidden, 1 encoding_shape (+ sigma head, no ReLU), 2 rgb.0 (+ rgb head, no operand).
+template <int KIND, int OFF>
+__device__ __forceinline__ void ts_epilogue32(const uint32_t (&rr)[32], const float* __restrict__ bias,
+                                              const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
+                                              HeadAcc& acc, uint32_t (&out)[32]) {
+    constexpr bool RELU = (KIND != 1);
+#pragma unroll
+    for (int j8 = 0; j8 < 4; ++j8) {
+        const int col = j8 * 8;
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+        uint64_t v[4];
+        v[0] = fadd2(pk2(rr[col + 0], rr[col + 1]), pk2f(b0.x, b0.y));
+        v[1] = fadd2(pk2(rr[col + 2], rr[col + 3]), pk2f(b0.z, b0.w));
+        v[2] = fadd2(pk2(rr[col + 4], rr[col + 5]), pk2f(b1.x, b1.y));
+        v[3] = fadd2(pk2(rr[col + 6], rr[col + 7]), pk2f(b1.z, b1.w));
+        if (KIND == 1) {        // sigma head on the fp32 feature (reference src/model.py:45)
+            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_sigma + col));
+            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_sigma + col + 4));
+            acc.sig2 = ffma2(v[0], pk2f(w0.x, w0.y), acc.sig2); acc.sig2 = ffma2(v[1], pk2f(w0.z, w0.w), acc.sig2);
+            acc.sig2 = ffma2(v[2], pk2f(w1.x, w1.y), acc.sig2); acc.sig2 = ffma2(v[3], pk2f(w1.z, w1.w), acc.sig2);
+        } else if (KIND == 2) { // rgb.2 on the fp32 hidden (reference src/model.py:52)
+            uint64_t h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { float lo, hi; unpk2(v[i], lo, hi); h[i] = pk2f(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_rgb2 + k * (kW / 2) + col));
+                const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_rgb2 + k * (kW / 2) + col + 4));
+                uint64_t& a = (k == 0) ? acc.r2 : (k == 1 ? acc.g2 : acc.b2);
+                a = ffma2(h[0], pk2f(w0.x, w0.y), a); a = ffma2(h[1], pk2f(w0.z, w0.w), a);
+                a = ffma2(h[2], pk2f(w1.x, w1.y), a); a = ffma2(h[3], pk2f(w1.z, w1.w), a);
+            }
+        }
+        if (KIND != 2) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) out[OFF + j8 * 4 + i] = cvt_bf16x2<RELU>(v[i]);
+        }
+    }
+}
+// One thread's 64 columns of an accumulator half: columns [c0, c0 + 64) of the layer.
+template <int KIND>
+__device__ __forceinline__ void ts_half(uint32_t taddr, int c0, const float* __restrict__ bias,
+                                        const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2, HeadAcc& acc,
+                                        uint32_t (&P)[32]) {
+    uint32_t ra[32], rb[32];
+    umma::tmem_ld32(taddr, ra);
+    umma::tmem_ld32(taddr + 32, rb);
+    umma::tmem_ld_wait();
+    ts_epilogue32<KIND, 0>(ra, bias + c0, w_sigma + c0, w_rgb2 + c0, acc, P);
+    ts_epilogue32<KIND, 16>(rb, bias + c0 + 32, w_sigma + c0 + 32, w_rgb2 + c0 + 32, acc, P);
+}
+__device__ __forceinline__ void ts_store_operand(uint32_t taddr, const uint32_t (&P)[32]) {
+    uint32_t lo[16], hi[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { lo[i] = P[i]; hi[i] = P[16 + i]; }
+    umma::tmem_st16(taddr, lo);
+    umma::tmem_st16(taddr + 16, hi);
+}
+
+__global__ void __launch_bounds__(kTsThreads, 1) k_render_fwd_ts(const __grid_constant__ FwdParams p, const int n_slots) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sW = smem;                                        // [n_slots][16 KB]
+    uint8_t* sXyz = sW + (size_t)n_slots * kSlot;              // [2][16 KB]
+    uint8_t* sDir = sXyz + 2 * kABlock;                        // [2][8 KB]
+    float4* sHead = (float4*)(sDir + 2 * kDirBlock);           // [2][128] partial heads of the second column-half warp
+    float4* sRing = sHead + 2 * kTileRows;                     // [ring_cap] per-sample (sigma, r, g, b)
+    TsBars* B = (TsBars*)((uint8_t*)sRing + (size_t)p.ring_cap * 16);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nl = p.n_layers;
+
+    // ---- this CTA's contiguous share of the work (same split as k_render_fwd) ----
+    int64_t row0 = 0, nrows = 0, ray0 = 0;
+    {
+        const int64_t b = (int64_t)blockIdx.x;
+        if (p.mode == 0) {
+            const int64_t base = p.n_rays / gridDim.x, rem = p.n_rays % gridDim.x;
+            ray0 = b * base + min(b, rem);
+            const int64_t nr = base + (b < rem ? 1 : 0);
+            row0 = ray0 * p.rs.N; nrows = nr * p.rs.N;
+        } else {
+            const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
+            const int64_t base = tiles / gridDim.x, rem = tiles % gridDim.x;
+            const int64_t t0 = b * base + min(b, rem);
+            const int64_t nt = base + (b < rem ? 1 : 0);
+            row0 = t0 * kTileRows;
+            nrows = min(p.S - row0, nt * kTileRows);
+            if (nrows < 0) nrows = 0;
+        }
+    }
+    const int T = (int)((nrows + kTileRows - 1) / kTileRows);
+    const int rounds = (T + 1) >> 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kTsMaxSlots; ++i) { umma::mbar_init(&B->full[i], 1); umma::mbar_init(&B->empty[i], 1); }
+        for (int g = 0; g < 2; ++g) {
+            umma::mbar_init(&B->pe_ready[g], 4); umma::mbar_init(&B->xyz_free[g], 1); umma::mbar_init(&B->dir_free[g], 1);
+            umma::mbar_init(&B->a_ready[g], 8);
+            umma::mbar_init(&B->d_full[g], 1); umma::mbar_init(&B->d_free[g], 8);
+            umma::mbar_init(&B->samp_full[g], 4); umma::mbar_init(&B->samp_free[g], 4);
+        }
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(&B->tmem_slot, 512);
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = B->tmem_slot;
+
+    if (warp == 0) {
+        // ===== weight producer: each stage of a layer once per tile PAIR, half-major (h, chunk) =====
+        int slot = 0; uint32_t ph = 0;
+        for (int r = 0; r < rounds; ++r)
+            for (int l = 0; l < nl; ++l) {
+                const FwdLayer& L = p.layers[l];
+                const uint8_t* src = p.packed + L.w_off;
+                for (int h = 0; h < L.n_halves; ++h)
+                    for (int c = 0; c < L.n_kchunks + L.has_dir; ++c) {
+                        const bool dir = c == L.n_kchunks;
+                        const uint32_t bytes = dir ? kSlot / 2 : kSlot;
+                        const size_t img = dir ? (size_t)(L.n_kchunks * L.n_halves + h) : (size_t)(c * L.n_halves + h);
+                        umma::mbar_wait(&B->empty[slot], ph ^ 1);
+                        if (umma::elect_one()) {
+                            umma::mbar_arrive_expect_tx(&B->full[slot], bytes);
+                            umma::bulk_g2s(sW + slot * kSlot, src + img * kSlot, bytes, &B->full[slot]);
+                        }
+                        __syncwarp();
+                        if (++slot == n_slots) { slot = 0; ph ^= 1; }
+                    }
+            }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        int slot = 0; uint32_t ph = 0;
+        uint32_t kd0 = 0, kd1 = 0;       // uses of D0 / D1 so far
+        uint32_t ua0 = 0, ua1 = 0;       // a_ready phases consumed per tile slot
+        CNB_TR_DECL(tr_wa); CNB_TR_DECL(tr_wd); CNB_TR_DECL(tr_ww); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
+        const uint32_t id128 = umma::make_idesc(128, 128, 0, 0);
+        const uint64_t dW = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
+        const uint64_t dWd = umma::make_sdesc(umma::smem_u32(sW), 16, 512, umma::SWZ_64B);
+        for (int r = 0; r < rounds; ++r) {
+            const int ntile = min(2, T - 2 * r);
+            for (int l = 0; l < nl; ++l) {
+                const FwdLayer& L = p.layers[l];
+                const int slot0 = slot; const uint32_t ph0 = ph;
+                for (int g = 0; g < ntile; ++g) {
+                    slot = slot0; ph = ph0;                       // tile Y walks the same stages again
+                    if (l == 0) CNB_TR(tr_wa, umma::mbar_wait(&B->pe_ready[g], (uint32_t)r & 1u));
+                    else if (g == 0) { CNB_TR(tr_wa, umma::mbar_wait(&B->a_ready[0], ua0 & 1u)); ++ua0; }
+                    else { CNB_TR(tr_wa, umma::mbar_wait(&B->a_ready[1], ua1 & 1u)); ++ua1; }
+                    const uint64_t dX = umma::make_sdesc(umma::smem_u32(sXyz + g * kABlock), 16, 1024, umma::SWZ_128B);
+                    const uint64_t dD = umma::make_sdesc(umma::smem_u32(sDir + g * kDirBlock), 16, 512, umma::SWZ_64B);
+                    const uint32_t aT = tmem + kColA + (uint32_t)g * 128u;
+                    const bool first = g == 0, last = g == ntile - 1;
+                    for (int h = 0; h < L.n_halves; ++h) {
+                        const uint32_t kd = h ? kd1 : kd0;
+                        CNB_TR(tr_wd, umma::mbar_wait(&B->d_free[h], (kd & 1u) ^ 1u));
+                        umma::tc_fence_after();
+                        const uint32_t dT = tmem + (uint32_t)h * 128u;
+                        for (int c = 0; c < L.n_kchunks; ++c) {
+                            if (first) { CNB_TR(tr_ww, umma::mbar_wait(&B->full[slot], ph)); umma::tc_fence_after(); }
+                            if (umma::elect_one()) {
+                                const uint64_t db = dW + (uint64_t)((slot * kSlot) >> 4);
+                                if (l == 0) {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma::mma_bf16(dT, dX + ks * 2, db + ks * 2, id128, (c | ks) ? 1u : 0u);
+                                } else {
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ++ks) umma::mma_bf16_ts(dT, aT + c * 32 + ks * 8, db + ks * 2, id128, (c | ks) ? 1u : 0u);
+                                }
+                                if (last) umma::mma_commit(&B->empty[slot]);
+                            }
+                            __syncwarp();
+                            if (++slot == n_slots) { slot = 0; ph ^= 1; }
+                        }
+                        if (L.has_dir) {
+                            if (first) { umma::mbar_wait(&B->full[slot], ph); umma::tc_fence_after(); }
+                            if (umma::elect_one()) {
+                                const uint64_t db = dWd + (uint64_t)((slot * kSlot) >> 4);
+#pragma unroll
+                                for (int ks = 0; ks < 2; ++ks) umma::mma_bf16(dT, dD + ks * 2, db + ks * 2, id128, 1u);
+                                if (last) umma::mma_commit(&B->empty[slot]);
+                            }
+                            __syncwarp();
+                            if (++slot == n_slots) { slot = 0; ph ^= 1; }
+                        }
+                        if (umma::elect_one()) umma::mma_commit(&B->d_full[h]);
+                        __syncwarp();
+                        if (h) ++kd1; else ++kd0;
+                    }
+                    if (umma::elect_one()) {
+                        if (l == 0) umma::mma_commit(&B->xyz_free[g]);
+                        if (L.has_dir) umma::mma_commit(&B->dir_free[g]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        CNB_TR_FLUSH(2, tr_wa); CNB_TR_FLUSH(3, tr_ww); CNB_TR_FLUSH(4, tr_tot); CNB_TR_FLUSH(13, tr_wd);
+    } else if (warp >= 4 && warp < 12) {
+        // ===== epilogue warps =====
+        const int q = warp & 3;                        // TMEM lane quarter
+        const int ch = (warp - 4) >> 2;                // which 64 of a half's 128 columns
+        const int row = q * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int N = p.rs.N;
+        uint32_t kd0 = 0, kd1 = 0;
+        uint64_t sigX = 0ull, sigY = 0ull;             // sigma-head partial of this thread's columns, per tile slot
+        CNB_TR_DECL(tr_w0); CNB_TR_DECL(tr_w1); CNB_TR_DECL(tr_fin); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
+        for (int r = 0; r < rounds; ++r) {
+            const int ntile = min(2, T - 2 * r);
+            for (int l = 0; l < nl; ++l) {
+                const FwdLayer& L = p.layers[l];
+                for (int g = 0; g < ntile; ++g) {
+                    const int t = 2 * r + g;
+                    const int64_t lrow = (int64_t)t * kTileRows + row;
+                    const bool valid = lrow < nrows;
+                    const int64_t grow = row0 + lrow;
+                    int64_t code = 0;
+                    if (p.n_codes > 1) {
+                        code = (p.ray_offset * N + (valid ? grow : row0)) / p.rows_per_code;
+                        if (code >= p.n_codes) code = p.n_codes - 1;
+                    }
+                    const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
+                    HeadAcc hacc = {g ? sigY : sigX, 0ull, 0ull, 0ull, 0ull};
+                    if (l == 0) hacc.sig2 = 0ull;
+                    uint32_t P[32];
+                    const uint32_t tD = tmem + lane_off + (uint32_t)ch * 64u;
+                    const uint32_t tA = tmem + lane_off + kColA + (uint32_t)g * 128u + (uint32_t)ch * 32u;
+                    // ---- half 0 ----
+                    CNB_TR(tr_w0, umma::mbar_wait(&B->d_full[0], kd0 & 1u)); ++kd0;
+                    umma::tc_fence_after();
+                    if (L.kind == 0) ts_half<0>(tD, ch * 64, bias, p.w_sigma, p.w_rgb2, hacc, P);
+                    else if (L.kind == 1) ts_half<1>(tD, ch * 64, bias, p.w_sigma, p.w_rgb2, hacc, P);
+                    else ts_half<2>(tD, ch * 64, bias, p.w_sigma, p.w_rgb2, hacc, P);
+                    umma::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) umma::mbar_arrive(&B->d_free[0]);
+                    if (L.n_halves == 2) {
+                        // ---- half 1: all MMAs of the layer have read A_tile, the operand may be rewritten ----
+                        CNB_TR(tr_w1, umma::mbar_wait(&B->d_full[1], kd1 & 1u)); ++kd1;
+                        umma::tc_fence_after();
+                        ts_store_operand(tA, P);
+                        if (L.kind == 0) ts_half<0>(tD + 128u, 128 + ch * 64, bias, p.w_sigma, p.w_rgb2, hacc, P);
+                        else ts_half<1>(tD + 128u, 128 + ch * 64, bias, p.w_sigma, p.w_rgb2, hacc, P);
+                        ts_store_operand(tA + 64u, P);
+                        umma::tmem_st_wait();
+                        umma::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) { umma::mbar_arrive(&B->d_free[1]); umma::mbar_arrive(&B->a_ready[g]); }
+                        if (g) sigY = hacc.sig2; else sigX = hacc.sig2;
+                        continue;
+                    }
+                    // ---- last layer (rgb.0, one half): heads -> per-sample outputs ----
+                    const long long tr_f0 = CNB_TR_NOW();
+                    float sig_p, cr, cg, cb;
+                    { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_p = a0 + a1; unpk2(hacc.r2, a0, a1); cr = a0 + a1;
+                      unpk2(hacc.g2, a0, a1); cg = a0 + a1; unpk2(hacc.b2, a0, a1); cb = a0 + a1; }
+                    if (ch == 1) sHead[g * kTileRows + row] = make_float4(sig_p, cr, cg, cb);
+                    umma::named_bar_sync(1, 256);
+                    if (ch == 0) {
+                        const float4 o = sHead[g * kTileRows + row];
+                        const float sigma = cnb_softplus(sig_p + o.x + __ldg(p.b_sigma));
+                        cr += o.y + __ldg(p.b_rgb2 + 0); cg += o.z + __ldg(p.b_rgb2 + 1); cb += o.w + __ldg(p.b_rgb2 + 2);
+                        if (p.mode == 1) {
+                            if (valid) {
+                                p.sigmas[grow] = sigma;
+                                p.rgbs[grow * 3 + 0] = cr; p.rgbs[grow * 3 + 1] = cg; p.rgbs[grow * 3 + 2] = cb;
+                            }
+                        } else {
+                            umma::mbar_wait(&B->samp_free[g], ((uint32_t)r & 1u) ^ 1u);   // tile t - 2 has been composited
+                            if (valid) {
+                                sRing[lrow % p.ring_cap] = make_float4(sigma, cr, cg, cb);
+                                if (p.spill_sig) {
+                                    p.spill_sig[grow] = sigma;
+                                    p.spill_rgb[grow * 3 + 0] = cr; p.spill_rgb[grow * 3 + 1] = cg; p.spill_rgb[grow * 3 + 2] = cb;
+                                }
+                            }
+                            __syncwarp();
+                            if (lane == 0) umma::mbar_arrive(&B->samp_full[g]);
+                        }
+                    }
+                    umma::named_bar_sync(1, 256);      // sHead[g] may be rewritten
+                    tr_fin += (unsigned long long)(CNB_TR_NOW() - tr_f0);
+                }
+            }
+        }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        if (warp == 4) { CNB_TR_FLUSH(5, tr_w0); CNB_TR_FLUSH(6, tr_w1); CNB_TR_FLUSH(7, tr_fin); CNB_TR_FLUSH(8, tr_tot); }
+    } else if (warp >= 12) {
+        // ===== ray / sample generation + positional encoding (two tiles ahead), compositing of finished tiles =====
+        const int iw = warp - 12;
+        const int row = iw * 32 + lane;
+        const int N = p.rs.N;
+        CNB_TR_DECL(tr_wx); CNB_TR_DECL(tr_ws); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
+        for (int i = 0; i < T + 2; ++i) {
+            if (i < T) {
+                const int g = i & 1; const uint32_t u = (uint32_t)(i >> 1);
+                const int64_t lrow = (int64_t)i * kTileRows + row;
+                const bool valid = lrow < nrows;
+                const int64_t grow = row0 + lrow;
+                float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+                if (valid) {
+                    if (p.mode == 0) {
+                        const int64_t lray = grow / N;
+                        const int zi = (int)(grow - lray * N);
+                        const int64_t ray = p.ray_offset + lray;
+                        float o[3];
+                        cnb_fetch_ray(p.rs, ray, o, dir);
+                        const int64_t seg = ray / p.rs.rays_per_segment;
+                        const float z = __ldg(p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0) + zi);
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + grow * 3 + k); dir[k] = __ldg(p.viewdir + grow * 3 + k); }
+                    }
+                }
+                CNB_TR(tr_wx, umma::mbar_wait(&B->xyz_free[g], (u & 1u) ^ 1u));       // layer 0 of the previous tile in this slot is done
+                encode_xyz_row(pos, valid, sXyz + g * kABlock, row);
+                CNB_TR(tr_wx, umma::mbar_wait(&B->dir_free[g], (u & 1u) ^ 1u));       // ... and its PE(viewdir) layer
+                encode_dir_row(dir, valid, sDir + g * kDirBlock, row);
+                umma::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&B->pe_ready[g]);
+            }
+            if (p.mode == 0 && i >= 2) {
+                const int t = i - 2, g = t & 1; const uint32_t u = (uint32_t)(t >> 1);
+                CNB_TR(tr_ws, umma::mbar_wait(&B->samp_full[g], u & 1u));
+                const int64_t tile_lo = (int64_t)t * kTileRows, tile_hi = min(tile_lo + kTileRows, nrows);
+                const int64_t q_first = tile_lo / N;        // first ray whose last row lies in this tile
+                const int64_t q_last = tile_hi / N - 1;     // last ray completed by the end of this tile
+                for (int64_t qr = q_first + iw; qr <= q_last; qr += 4)
+                    composite_ray(p, sRing, p.ring_cap, qr * N, p.ray_offset + ray0 + qr, lane);
+                __syncwarp();
+                if (lane == 0) umma::mbar_arrive(&B->samp_free[g]);
+            }
+        }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        if (warp == 12) { CNB_TR_FLUSH(9, tr_wx); CNB_TR_FLUSH(10, tr_ws); CNB_TR_FLUSH(11, tr_tot); }
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------
@@ -410,27 +816,41 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
     static const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();
-    if (use_pairs && grid >= 2) {
-        grid &= ~1;
-        CNB_TRY(make_weight_maps(packed, pl.total_bytes, &fp.maps));
-        CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+    const char* form = getenv("CNB_FWD_KERNEL");       // "ts" (default): operands in tensor memory; "ss": in shared memory
+    if (!use_pairs && !(form && form[0] == 's')) {
+        int n_slots = kTsMaxSlots;
+        auto need = [&](int slots) {
+            return 1024 + (size_t)slots * kSlot + 2 * (size_t)kABlock + 2 * (size_t)kDirBlock + 2 * kTileRows * sizeof(float4) +
+                   (size_t)fp.ring_cap * 16 + sizeof(TsBars) + 64;
+        };
+        while (n_slots > 8 && need(n_slots) > 232448) --n_slots;
+        if (need(n_slots) > 232448) return CNB_E_UNSUPPORTED;
+        const size_t tsmem = need(n_slots);
+        CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsmem));
         cnb_prof_begin(CNB_K_FWD, st);
-        const cudaError_t e = cudaLaunchKernelEx(&cfg, k_render_fwd<2>, fp);
+        k_render_fwd_ts<<<grid, kTsThreads, tsmem, st>>>(fp, n_slots);
         cnb_prof_end(CNB_K_FWD, st);
-        if (e != cudaSuccess) return (int)e;
         CNB_LAUNCH_CHECK();
         return CNB_OK;
     }
-    CNB_CUDA_TRY(cudaFuncSetAttribute(k_render_fwd<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int mc = (grid == sms && !use_pairs) ? weight_multicast() : 1;
+    const bool pairs = use_pairs && grid >= 2;
+    if (pairs) { grid &= ~1; CNB_TRY(make_weight_maps(packed, pl.total_bytes, &fp.maps)); }
+    void (*kern)(const FwdParams) = pairs ? k_render_fwd<2, 1> : mc == 4 ? k_render_fwd<1, 4> : mc == 2 ? k_render_fwd<1, 2> : k_render_fwd<1, 1>;
+    const int csize = pairs ? 2 : mc;
+    CNB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = csize > 1 ? 1 : 0;
+    if (mc > 1) CNB_TRY(cluster_grid(kern, &cfg, mc, &grid));
+    cfg.gridDim = dim3(grid);
     cnb_prof_begin(CNB_K_FWD, st);
-    k_render_fwd<1><<<grid, kThreads, smem, st>>>(fp);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, fp);
     cnb_prof_end(CNB_K_FWD, st);
+    if (e != cudaSuccess) return (int)e;
     CNB_LAUNCH_CHECK();
     return CNB_OK;
 }

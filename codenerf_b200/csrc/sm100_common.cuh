@@ -4,6 +4,7 @@
 #include "render_sm100.cuh"
 #include "mlp_fp32.cuh"
 #include <cuda.h>
+#include <cstdlib>
 #include "umma.cuh"
 #include <type_traits>
 
@@ -20,6 +21,21 @@ constexpr int kDirBlock = 8192;         // PE(viewdir) block [128 rows x 32] bf1
 constexpr int kATile = 4 * kABlock + kDirBlock;
 constexpr int kThreads = 320;           // warp 0 producer, warp 1 MMA, warps 2-5 group X, 6-9 group Y
 constexpr int kMaxLayers = 2 * CNB_MAX_BLOCKS + 4;
+
+// ---- optional cycle accounting of the pipeline roles (build with -DCNB_TRACE; debugging only) ----------
+#ifdef CNB_TRACE
+static __device__ unsigned long long g_trace[32];   // one copy per translation unit
+#define CNB_TR_NOW() clock64()
+#define CNB_TR_DECL(name) unsigned long long name = 0ull
+#define CNB_TR(acc, ...) do { const long long t_ = clock64(); __VA_ARGS__; (acc) += (unsigned long long)(clock64() - t_); } while (0)
+#define CNB_TR_PTR(ptr, ...) do { const long long t_ = clock64(); __VA_ARGS__; if (ptr) *(ptr) += (unsigned long long)(clock64() - t_); } while (0)
+#define CNB_TR_FLUSH(slot, acc) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_trace[slot], (acc)); } while (0)
+#else
+#define CNB_TR_NOW() 0ll
+#define CNB_TR_DECL(name) unsigned long long name = 0ull; (void)name
+#define CNB_TR(acc, ...) do { __VA_ARGS__; } while (0)
+#define CNB_TR_FLUSH(slot, acc) do { } while (0)
+#endif
 
 struct FwdLayer {
     uint32_t w_off;       // byte offset of the first stage slot inside the packed buffer
@@ -68,6 +84,24 @@ __device__ __forceinline__ void st_shared_v4_off(uint32_t addr, uint32_t a, uint
                  : "memory");
 }
 
+// Vector load of 4 floats that every lane reads from the same address (bias / head-weight rows).  SM = true: `p`
+// carries a shared-window address (see smem_fptr) and the load is an LDS broadcast; false: read-only global load.
+// The global form misses the small L1 left beside 220 KB of shared memory, and 64 such loads per layer with the
+// few registers available to prefetch them were the dominant stall of the epilogues (ncu source view, round 1).
+template <bool SM>
+__device__ __forceinline__ float4 ld_vec4(const float* p) {
+    if (SM) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                     : "r"((uint32_t)(uintptr_t)p));
+        return v;
+    }
+    return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ const float* smem_fptr(const void* shared_ptr) {
+    return reinterpret_cast<const float*>((uintptr_t)umma::smem_u32(shared_ptr));
+}
+
 // Accumulators of the narrow heads carried across a layer's epilogue as packed pairs.
 struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 
@@ -76,7 +110,7 @@ struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 // the next operand, [ReLU sign bits for the backward].   KIND: 0 hidden, 1 encoding_shape
 // (+ sigma head, no ReLU), 2 rgb.0 (+ rgb head).   a8[c] = shared address of 16-byte chunk c of
 // this row inside K-block 0.
-template <int CC, int KIND, bool STORE, bool MASK>
+template <int CC, int KIND, bool STORE, bool MASK, bool SM = false>
 __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const float* __restrict__ bias,
                                                const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
@@ -86,24 +120,26 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
     for (int j8 = 0; j8 < 4; ++j8) {
         constexpr int dummy = 0; (void)dummy;
         const int col = CC * 32 + j8 * 8;
-        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + col));
-        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + col + 4));
+        const float4 b0 = ld_vec4<SM>(bias + col);
+        const float4 b1 = ld_vec4<SM>(bias + col + 4);
         uint64_t v[4];
         v[0] = fadd2(pk2(rr[j8 * 8 + 0], rr[j8 * 8 + 1]), pk2f(b0.x, b0.y));
         v[1] = fadd2(pk2(rr[j8 * 8 + 2], rr[j8 * 8 + 3]), pk2f(b0.z, b0.w));
         v[2] = fadd2(pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]), pk2f(b1.x, b1.y));
         v[3] = fadd2(pk2(rr[j8 * 8 + 6], rr[j8 * 8 + 7]), pk2f(b1.z, b1.w));
         if (MASK && RELU) {     // collect the sign bits of the pre-activations (column c -> bit 31 - c%32)
+            uint32_t s8 = 0u;   // 8 bits per group: four short dependency chains instead of one 32-deep chain
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 float lo, hi; unpk2(v[i], lo, hi);
-                sgn = __funnelshift_l(__float_as_uint(lo), sgn, 1);
-                sgn = __funnelshift_l(__float_as_uint(hi), sgn, 1);
+                s8 = __funnelshift_l(__float_as_uint(lo), s8, 1);
+                s8 = __funnelshift_l(__float_as_uint(hi), s8, 1);
             }
+            sgn = (sgn << 8) | s8;
         }
         if (KIND == 1) {        // sigma head on the fp32 feature (reference src/model.py:45)
-            const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_sigma + col));
-            const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_sigma + col + 4));
+            const float4 w0 = ld_vec4<SM>(w_sigma + col);
+            const float4 w1 = ld_vec4<SM>(w_sigma + col + 4);
             acc.sig2 = ffma2(v[0], pk2f(w0.x, w0.y), acc.sig2); acc.sig2 = ffma2(v[1], pk2f(w0.z, w0.w), acc.sig2);
             acc.sig2 = ffma2(v[2], pk2f(w1.x, w1.y), acc.sig2); acc.sig2 = ffma2(v[3], pk2f(w1.z, w1.w), acc.sig2);
         } else if (KIND == 2) { // rgb.2 on the fp32 hidden (reference src/model.py:52)
@@ -112,8 +148,8 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
             for (int i = 0; i < 4; ++i) { float lo, hi; unpk2(v[i], lo, hi); h[i] = pk2f(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4 w0 = __ldg(reinterpret_cast<const float4*>(w_rgb2 + k * (kW / 2) + col));
-                const float4 w1 = __ldg(reinterpret_cast<const float4*>(w_rgb2 + k * (kW / 2) + col + 4));
+                const float4 w0 = ld_vec4<SM>(w_rgb2 + k * (kW / 2) + col);
+                const float4 w1 = ld_vec4<SM>(w_rgb2 + k * (kW / 2) + col + 4);
                 uint64_t& a = (k == 0) ? acc.r2 : (k == 1 ? acc.g2 : acc.b2);
                 a = ffma2(h[0], pk2f(w0.x, w0.y), a); a = ffma2(h[1], pk2f(w0.z, w0.w), a);
                 a = ffma2(h[2], pk2f(w1.x, w1.y), a); a = ffma2(h[3], pk2f(w1.z, w1.w), a);
@@ -130,7 +166,7 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
 }
 
 // A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.
-template <int NCC, int KIND, bool STORE, bool MASK>
+template <int NCC, int KIND, bool STORE, bool MASK, bool SM = false>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                    const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
@@ -140,8 +176,8 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         umma::tmem_ld32(taddr + CC * 32, ra);
         umma::tmem_ld32(taddr + CC * 32 + 32, rb);
         umma::tmem_ld_wait();
-        fwd_epilogue32<CC, KIND, STORE, MASK>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<CC + 1, KIND, STORE, MASK>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -156,14 +192,30 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
 // a single elected lane issues the asynchronous instructions.
 
 // Stream `n_stages` consecutive weight stage images (the last `n_small` of them half-size) into the ring.
+// MC > 1: the CTAs of a cluster of MC consume the SAME stage sequence; ring slot i is filled for all of them by
+// CTA (i mod MC) with one multicast bulk copy (w_empty then counts the MMA commits of all MC CTAs), so every
+// weight byte leaves L2 once per cluster instead of once per CTA.
+template <int MC = 1>
 __device__ __forceinline__ void produce_stages(const uint8_t* __restrict__ src, int n_stages, int n_small, uint8_t* sW,
-                                               uint64_t* w_full, uint64_t* w_empty, int& stage, uint32_t& ph) {
+                                               uint64_t* w_full, uint64_t* w_empty, int& stage, uint32_t& ph,
+                                               uint32_t rank = 0, unsigned long long* tr_wait = nullptr, uint64_t l2_policy = 0ull) {
+    static_assert(MC == 1 || kNumStages % MC == 0, "ring slots map to issuing CTAs by slot index");
     for (int s = 0; s < n_stages; ++s) {
+#ifdef CNB_TRACE
+        CNB_TR_PTR(tr_wait, umma::mbar_wait(&w_empty[stage], ph ^ 1));
+#else
         umma::mbar_wait(&w_empty[stage], ph ^ 1);
+#endif
         if (umma::elect_one()) {
             const uint32_t bytes = s < n_stages - n_small ? kSlot : kSlot / 2;
             umma::mbar_arrive_expect_tx(&w_full[stage], bytes);
-            umma::bulk_g2s(sW + stage * kSlot, src + (size_t)s * kSlot, bytes, &w_full[stage]);
+            if (MC == 1) {
+                if (l2_policy) umma::bulk_g2s_hint(sW + stage * kSlot, src + (size_t)s * kSlot, bytes, &w_full[stage], l2_policy);
+                else umma::bulk_g2s(sW + stage * kSlot, src + (size_t)s * kSlot, bytes, &w_full[stage]);
+            } else if ((uint32_t)(stage & (MC - 1)) == rank) {
+                if (l2_policy) umma::bulk_g2s_mcast_hint(sW + stage * kSlot, src + (size_t)s * kSlot, bytes, &w_full[stage], (uint16_t)((1u << MC) - 1u), l2_policy);
+                else umma::bulk_g2s_mcast(sW + stage * kSlot, src + (size_t)s * kSlot, bytes, &w_full[stage], (uint16_t)((1u << MC) - 1u));
+            }
         }
         __syncwarp();
         if (++stage == kNumStages) { stage = 0; ph ^= 1; }
@@ -173,24 +225,33 @@ __device__ __forceinline__ void produce_stages(const uint8_t* __restrict__ src, 
 // Issue one GEMM of one tile: D[128 x (128*n_halves)] = A[128 x 64*n_kchunks (+32)] . B^T.
 // A = K-blocks 0.. of the tile's operand buffer (+ the PE(viewdir) block); B = ring stages in the
 // order (chunk, half).  With two halves the pair of adjacent stages is one N = 256 operand.
+template <int MC = 1>
+__device__ __forceinline__ void release_slot(uint64_t* bar) {
+    if (MC == 1) umma::mma_commit(bar); else umma::mma_commit_mcast(bar, (uint16_t)((1u << MC) - 1u));
+}
+template <int MC = 1>
 __device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t d_base, uint8_t* sW, uint64_t* w_full,
                                            uint64_t* w_empty, int n_kchunks, int n_halves, int has_dir, int& stage,
-                                           uint32_t& ph, uint64_t* done_bar) {
+                                           uint32_t& ph, uint64_t* done_bar, unsigned long long* tr_wait = nullptr) {
     const uint64_t dA = umma::make_sdesc(a_base, 16, 1024, umma::SWZ_128B);
     const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
     if (n_halves == 2) {
         const uint32_t idesc = umma::make_idesc(128, 256, 0, 0);
         for (int c = 0; c < n_kchunks; ++c) {
+#ifdef CNB_TRACE
+            CNB_TR_PTR(tr_wait, umma::mbar_wait(&w_full[stage], ph); umma::mbar_wait(&w_full[stage + 1], ph));
+#else
             umma::mbar_wait(&w_full[stage], ph);
             umma::mbar_wait(&w_full[stage + 1], ph);
+#endif
             umma::tc_fence_after();
             if (umma::elect_one()) {
                 const uint64_t da = dA + (uint64_t)((c * kABlock) >> 4);
                 const uint64_t db = dB + (uint64_t)((stage * kSlot) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) umma::mma_bf16(d_base, da + ks * 2, db + ks * 2, idesc, (c | ks) ? 1u : 0u);
-                umma::mma_commit(&w_empty[stage]);
-                umma::mma_commit(&w_empty[stage + 1]);
+                release_slot<MC>(&w_empty[stage]);
+                release_slot<MC>(&w_empty[stage + 1]);
             }
             __syncwarp();
             stage += 2;
@@ -206,7 +267,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t d_base, uin
                 const uint64_t db = dB + (uint64_t)((stage * kSlot) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks) umma::mma_bf16(d_base, da + ks * 2, db + ks * 2, idesc, (c | ks) ? 1u : 0u);
-                umma::mma_commit(&w_empty[stage]);
+                release_slot<MC>(&w_empty[stage]);
             }
             __syncwarp();
             if (++stage == kNumStages) { stage = 0; ph ^= 1; }
@@ -223,7 +284,7 @@ __device__ __forceinline__ void issue_gemm(uint32_t a_base, uint32_t d_base, uin
                 const uint64_t db = dBd + (uint64_t)((stage * kSlot) >> 4);
 #pragma unroll
                 for (int ks = 0; ks < 2; ++ks) umma::mma_bf16(d_base + h * 128, dAd + ks * 2, db + ks * 2, idesc, 1u);
-                umma::mma_commit(&w_empty[stage]);
+                release_slot<MC>(&w_empty[stage]);
             }
             __syncwarp();
             if (++stage == kNumStages) { stage = 0; ph ^= 1; }
@@ -264,12 +325,17 @@ __device__ __forceinline__ void produce_stages_2cta(const WeightMaps* maps, uint
 // leader CTA: issue one GEMM for the pair's two tiles (M = 256)
 __device__ __forceinline__ void issue_gemm_2cta(uint32_t a_base, uint32_t d_base, uint8_t* sW, uint64_t* w_full,
                                                 uint64_t* w_empty, int n_kchunks, int n_halves,
-                                                int has_dir, int& stage, uint32_t& ph, uint64_t* done_bar) {
+                                                int has_dir, int& stage, uint32_t& ph, uint64_t* done_bar,
+                                                unsigned long long* tr_wait = nullptr) {
     const uint64_t dA = umma::make_sdesc(a_base, 16, 1024, umma::SWZ_128B);
     const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
     const uint32_t idesc = umma::make_idesc(256, n_halves * 128, 0, 0);
     for (int c = 0; c < n_kchunks; ++c) {
+#ifdef CNB_TRACE
+        CNB_TR_PTR(tr_wait, umma::mbar_wait_cluster(&w_full[stage], ph));
+#else
         umma::mbar_wait_cluster(&w_full[stage], ph);
+#endif
         umma::tc_fence_after();
         if (umma::elect_one()) {
             const uint64_t da = dA + (uint64_t)((c * kABlock) >> 4);
@@ -301,8 +367,8 @@ __device__ __forceinline__ void issue_gemm_2cta(uint32_t a_base, uint32_t d_base
 
 // PE of one row into the operand blocks -- reference src/model.py:4-7 (x, sines, cosines).
 // sin/cos(2^i x) by exact doubling from an accurate sincosf(x): error < 2^i * 1e-7, far below bf16.
-__device__ __forceinline__ void encode_row(const float p[3], const float v[3], bool valid, uint8_t* blk0,
-                                           uint8_t* dirblk, int row) {
+// xyz: 63 channels (+1 zero) -> row `row` of a [128 x 64] bf16 block, 128-byte swizzle.
+__device__ __forceinline__ void encode_xyz_row(const float p[3], bool valid, uint8_t* blk0, int row) {
     float e[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) e[i] = 0.f;
@@ -328,6 +394,9 @@ __device__ __forceinline__ void encode_row(const float p[3], const float v[3], b
                      umma::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]), umma::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]),
                      umma::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
     }
+}
+// view direction: 27 channels (+5 zeros) -> row `row` of a [128 x 32] bf16 block, 64-byte swizzle.
+__device__ __forceinline__ void encode_dir_row(const float v[3], bool valid, uint8_t* dirblk, int row) {
     float d[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) d[i] = 0.f;
@@ -353,6 +422,11 @@ __device__ __forceinline__ void encode_row(const float p[3], const float v[3], b
                      umma::pack_bf16(d[ch * 8 + 2], d[ch * 8 + 3]), umma::pack_bf16(d[ch * 8 + 4], d[ch * 8 + 5]),
                      umma::pack_bf16(d[ch * 8 + 6], d[ch * 8 + 7]));
     }
+}
+__device__ __forceinline__ void encode_row(const float p[3], const float v[3], bool valid, uint8_t* blk0,
+                                           uint8_t* dirblk, int row) {
+    encode_xyz_row(p, valid, blk0, row);
+    encode_dir_row(v, valid, dirblk, row);
 }
 
 
@@ -391,6 +465,26 @@ inline int make_plan(const cnb_net_config* c, const float* const* P, Plan* pl) {
         off += (size_t)(pl->fwd[l].n_halves * 2) * 2 * kSlot;
     }
     pl->total_bytes = off;
+    return CNB_OK;
+}
+
+// CNB_WEIGHT_MCAST = 1 | 2 | 4: CTAs per cluster sharing one multicast weight stream (full-grid launches only).
+inline int weight_multicast() {
+    const char* e = getenv("CNB_WEIGHT_MCAST");      // read per launch: tests switch it inside one process
+    const int m = e ? atoi(e) : 1;
+    return (m == 2 || m == 4) ? m : 1;
+}
+// Largest grid (a multiple of the cluster size) whose clusters are all co-resident: the kernels are persistent
+// and split the work by gridDim, so a second wave of clusters would double the run time.
+template <class K>
+inline int cluster_grid(K kern, cudaLaunchConfig_t* cfg, int csize, int* grid) {
+    int n = 0;
+    cfg->gridDim = dim3((unsigned)((*grid / csize) * csize));
+    CNB_CUDA_TRY(cudaOccupancyMaxActiveClusters(&n, kern, cfg));
+    if (n < 1) return CNB_E_DEVICE;
+    int g = *grid / csize;
+    if (g > n) g = n;
+    *grid = g * csize;
     return CNB_OK;
 }
 
