@@ -40,6 +40,7 @@ struct FwdParams {
     int64_t n_rays, S;            // rays / rows of THIS launch
     int64_t ray_offset;           // mode 0: global index of this launch's first ray (sub-batching)
     int white_bg, ring_cap;
+    int stage_bias;               // 1: shared memory has room for the bias / head-weight staging area
     float *rgb, *depth, *acc;
     float *spill_sig, *spill_rgb; // optional per-sample spill (launch-relative rows) for the training backward
     float *sigmas, *rgbs;
@@ -120,6 +121,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     uint64_t* w_full_peer = acc_full + 2;        // [kNumStages] (leader of a CTA pair): the peer's half has landed
     uint32_t* tmem_slot = (uint32_t*)(w_full_peer + kNumStages);
     volatile int* final_count = (volatile int*)(tmem_slot + 2);
+    float* sBias = (float*)(tmem_slot + 8);      // [2 groups][2 buffers][256], then sigma-head [256] and rgb.2 [3][128] weights
+    float* sWsig = sBias + 4 * kW;
+    float* sWrgb = sWsig + kW;
     const uint32_t rank = kCluster > 1 ? umma::cluster_ctarank() : 0u;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -158,6 +162,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         umma::fence_mbar_init();
     }
     if (warp == 1) { if (CG == 2) umma::tmem_alloc2(tmem_slot, 512); else umma::tmem_alloc(tmem_slot, 512); }
+    if (p.stage_bias) {
+        for (int i = threadIdx.x; i < kW; i += kThreads) sWsig[i] = __ldg(p.w_sigma + i);
+        for (int i = threadIdx.x; i < 3 * (kW / 2); i += kThreads) sWrgb[i] = __ldg(p.w_rgb2 + i);
+    }
     umma::tc_fence_before();
     if (kCluster > 1) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
@@ -218,6 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         for (int c = 0; c < 8; ++c) a8[c] = umma::smem_u32(sA + row * 128 + ((c ^ (row & 7)) << 4));
         CNB_TR_DECL(tr_wacc); CNB_TR_DECL(tr_epi); CNB_TR_DECL(tr_enc); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
+        const int tg = wi * 32 + lane;               // thread index inside the group
+        uint32_t bsel = 0;                           // bias staging buffer of the next layer (alternates)
         for (int r = 0; r < rounds; ++r) {
             const int t = 2 * r + g;
             if (t >= T) break;
@@ -256,15 +266,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
             tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
             HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, 0ull};
+            // bias rows go through shared memory when the whole tile uses one code (always, unless a tile straddles objects)
+            bool staged = p.stage_bias != 0;
+            int64_t code_b = code;                   // code whose bias rows this thread reads (staged: the tile's code)
+            if (staged && p.n_codes > 1) {
+                const int64_t last_l = min((int64_t)t * kTileRows + kTileRows, nrows) - 1;
+                const int64_t c_lo = min((p.ray_offset * N + row0 + (int64_t)t * kTileRows) / p.rows_per_code, (int64_t)p.n_codes - 1);
+                const int64_t c_hi = min((p.ray_offset * N + row0 + last_l) / p.rows_per_code, (int64_t)p.n_codes - 1);
+                staged = c_lo == c_hi;
+                if (staged) code_b = c_lo;
+            }
             for (int l = 0; l < nl; ++l) {
                 const FwdLayer& L = p.layers[l];
+                const float* bias = L.folded >= 0 ? p.folded + ((size_t)code_b * p.n_folded + L.folded) * kW : L.bias;
+                float2 bias2 = make_float2(0.f, 0.f);
+                const bool mine = 2 * tg < L.n_halves * 128;
+                if (staged && mine) bias2 = __ldg(reinterpret_cast<const float2*>(bias) + tg);    // in flight during the wait
                 CNB_TR(tr_wacc, umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u));
                 const long long tr_p0 = CNB_TR_NOW();
                 umma::tc_fence_after();
-                const float* bias = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
-                if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
-                else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
-                else fwd_epilogue_layer<4, 2, false, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                if (staged) {
+                    float* sb = sBias + (g * 2 + bsel) * kW; bsel ^= 1u;
+                    if (mine) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
+                    umma::named_bar_sync(1 + g, 128);
+                    const float* bs = smem_fptr(sb);
+                    const float* ws = smem_fptr(sWsig);
+                    const float* wr = smem_fptr(sWrgb);
+                    if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                    else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                    else fwd_epilogue_layer<4, 2, false, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                } else {
+                    if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                    else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                    else fwd_epilogue_layer<4, 2, false, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
+                }
                 if (l + 1 < nl) {
                     umma::tc_fence_before();
                     umma::fence_proxy_async_smem();
@@ -807,8 +842,11 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     fp.w_rgb2 = P[L.i_rgb2]; fp.b_rgb2 = P[L.i_rgb2 + 1];
     const int N = fp.mode == 0 ? fp.rs.N : 1;
     fp.ring_cap = fp.mode == 0 ? N + 384 : 16;
-    const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + (size_t)fp.ring_cap * 16 + 256;
+    size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + (size_t)fp.ring_cap * 16 + 256;
     if (smem > 232448) return CNB_E_UNSUPPORTED;
+    const size_t staging = sizeof(float) * (4 * kW + kW + 3 * (kW / 2));
+    fp.stage_bias = smem + staging <= 232448 ? 1 : 0;       // very long rays (N > ~300) leave no room: global bias loads
+    if (fp.stage_bias) smem += staging;
     int dev = 0, sms = 0;
     CNB_CUDA_TRY(cudaGetDevice(&dev));
     CNB_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
@@ -816,8 +854,8 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
     static const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();
-    const char* form = getenv("CNB_FWD_KERNEL");       // "ts" (default): operands in tensor memory; "ss": in shared memory
-    if (!use_pairs && !(form && form[0] == 's')) {
+    const char* form = getenv("CNB_FWD_KERNEL");       // "ts": the tensor-memory operand experiment (slower)
+    if (!use_pairs && form && form[0] == 't') {
         int n_slots = kTsMaxSlots;
         auto need = [&](int slots) {
             return 1024 + (size_t)slots * kSlot + 2 * (size_t)kABlock + 2 * (size_t)kDirBlock + 2 * kTileRows * sizeof(float4) +
