@@ -354,10 +354,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     blocks = B.out_blocks; out_layer = B.out_layer;
                     dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
                 }
-                if (stash && lane == 0) {
-                    umma::bulk_s2g_hint(dst, sA, (uint32_t)blocks * kABlock, pol_stream);
+                if (stash) {
+                    // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
+                    // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
+                    const uint32_t piece = (uint32_t)blocks * (kABlock / 32);
+                    umma::bulk_s2g_hint(dst + (size_t)lane * piece, sA + (size_t)lane * piece, piece, pol_stream);
                     if (phs == 0)
-                        umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
+                        umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot + lane * (kDirBlock / 32),
+                                            sA + 4 * kABlock + lane * (kDirBlock / 32), kDirBlock / 32, pol_stream);
                     umma::bulk_commit();
                 }
                 if (!phantom && out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
@@ -376,12 +380,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                     for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
                 }
-                if (stash && lane == 0) umma::bulk_wait_read_all();
+                if (stash) umma::bulk_wait_read_all();
                 __syncwarp();
                 if (lane == 0) umma::mbar_arrive(&buf_free[g]);
             }
         }
-        if (p.stash && lane == 0) umma::bulk_wait_all();
+        if (p.stash) umma::bulk_wait_all();
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         if (g == 0) { CNB_TR_FLUSH(3, tr_wx); CNB_TR_FLUSH(4, tr_tot); }
     } else {
