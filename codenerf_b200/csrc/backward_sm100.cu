@@ -29,7 +29,7 @@ extern "C" int cnb_debug_trace_bwd(unsigned long long* out32, int reset) {
 
 namespace {
 
-constexpr int kBwdThreads = 384;   // warp 0 producer, 1 MMA, 2-5 group X, 6-9 group Y, 10/11 aux X/Y
+constexpr int kBwdThreads = 384;   // warp 0 producer, 1 MMA, 2/3 aux X/Y, 4-7 group X, 8-11 group Y
 
 struct BwdStep {
     uint32_t w_off;       // W^T stage images of the layer this step back-propagates through (step >= 1)
@@ -285,9 +285,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     if (MC > 1) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const float* wsig_s = smem_fptr(sWsig);
-    const float* wrgb_s = smem_fptr(sWrgb);
 
+    if (warp < 4) {
+    umma::setmaxnreg_dec<kRegsAux>();
     if (warp == 0) {
         // ===== weight producer =====
         int stage = 0; uint32_t ph = 0;
@@ -324,9 +324,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(0, tr_wa); CNB_TR_FLUSH(1, tr_ww); CNB_TR_FLUSH(2, tr_tot);
-    } else if (warp >= 10) {
+    } else {
         // ===== auxiliary warps: operand stash (TMA bulk stores) and column sums of every dY =====
-        const int g = warp - 10;
+        const int g = warp - 2;
         const uint8_t* sA = sA0 + g * kATile;
         uint32_t ap = 0;
         const uint64_t pol_stream = umma::l2_policy_evict_first();   // the stash is written once and read by a later kernel
@@ -388,9 +388,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         if (p.stash) umma::bulk_wait_all();
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         if (g == 0) { CNB_TR_FLUSH(3, tr_wx); CNB_TR_FLUSH(4, tr_tot); }
+    }
     } else {
+        umma::setmaxnreg_inc<kRegsCompute>();
         // ===== compute groups =====
-        const int g = (warp - 2) >> 2;
+        const int g = (warp - 4) >> 2;
         const int q = warp & 3;
         const int row = q * 32 + lane;
         uint8_t* sA = sA0 + g * kATile;
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
         uint32_t opc = 0;     // accumulator phases consumed
         uint32_t* mscr = p.mask_scratch + ((size_t)(blockIdx.x * 2 + g) * nl) * 8 * kTileRows + row;
-        const int tg = ((warp - 2) & 3) * 32 + lane;     // thread index inside the group
+        const int tg = (warp & 3) * 32 + lane;           // thread index inside the group
         float* sB = sBias + g * 2 * kW;
         uint32_t bsel = 0;                               // staging buffer of the next layer (alternates)
 
@@ -473,8 +475,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 // the layer's bias row goes through shared memory: 2 floats per thread, then LDS broadcasts
                 float* sb = sB + bsel * kW; bsel ^= 1u;
                 if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
-                umma::named_bar_sync(1 + g, 128);
-                const float* bias = smem_fptr(sb);
+                const uint32_t tok = bar_sync_token(1 + g, 128);
+                const float* bias = smem_fptr(sb, tok);
+                const float* wsig_s = smem_fptr(sWsig, tok);     // per-layer token: the staged rows are read inside this layer
+                const float* wrgb_s = smem_fptr(sWrgb, tok);     // (an invariant address would be hoisted out of the tile loop)
                 uint32_t* ml = mscr + (size_t)l * 8 * kTileRows;
                 if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                 else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
@@ -503,7 +507,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 umma::named_bar_sync(1 + g, 128);
                 const int rays_in_tile = kTileRows / N;
                 const int64_t ray_base = phantom ? p.n_rays_total : (p.row_offset + (tile0 + t) * kTileRows) / N;
-                for (int k = (warp - 2) & 3; k < rays_in_tile; k += 4)
+                for (int k = warp & 3; k < rays_in_tile; k += 4)
                     composite_fwd_bwd(p, samp + k * N, seed + k * N, ray_base + k, lane);
                 umma::named_bar_sync(1 + g, 128);
                 const float4 sd = seed[row];
@@ -519,6 +523,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
             wait_buf_free();
             {
+                const float* wrgb_s = smem_fptr(sWrgb, order_token());
                 const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
                 uint32_t mlast = 0u;
 #pragma unroll
@@ -555,6 +560,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 umma::tc_fence_after();
                 wait_buf_free();
                 const uint32_t* ml = mscr + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
+                const float* wsig_s = smem_fptr(sWsig, order_token());
                 if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                 else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                 else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
@@ -563,7 +569,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             }
         }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
-        if (warp == 2) {
+        if (warp == 4) {
             CNB_TR_FLUSH(5, tr_wbuf); CNB_TR_FLUSH(6, tr_wacc_f); CNB_TR_FLUSH(7, tr_epi_f); CNB_TR_FLUSH(8, tr_mid);
             CNB_TR_FLUSH(9, tr_wacc_b); CNB_TR_FLUSH(10, tr_epi_b); CNB_TR_FLUSH(11, tr_enc); CNB_TR_FLUSH(12, tr_tot);
         }

@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     // a_ready lives in the leader CTA: the partner's compute warps arrive on it remotely
     const uint32_t a_ready_addr0 = CG == 2 ? umma::mapa(umma::smem_u32(&a_ready[0]), 0) : 0u;
 
+    if (warp < 4) {
+    umma::setmaxnreg_dec<kRegsAux>();
     if (warp == 0) {
         // ===== weight producer: TMA-engine bulk copies of stage images into the ring =====
         int stage = 0; uint32_t ph = 0;
@@ -212,11 +214,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(2, tr_wa); CNB_TR_FLUSH(3, tr_ww); CNB_TR_FLUSH(4, tr_tot);
+    }
     } else {
+        umma::setmaxnreg_inc<kRegsCompute>();
         // ===== compute groups: PE, per-layer epilogues (TMEM -> bias/ReLU -> bf16 operand), heads, compositing =====
-        const int g = (warp - 2) >> 2;
+        const int g = (warp - 4) >> 2;
         const int q = warp & 3;                  // TMEM lane quarter this warp may access
-        const int wi = (warp - 2) & 3;
+        const int wi = q;
         const int row = q * 32 + lane;
         uint8_t* sA = sA0 + g * kATile;
         const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
@@ -288,10 +292,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 if (staged) {
                     float* sb = sBias + (g * 2 + bsel) * kW; bsel ^= 1u;
                     if (mine) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
-                    umma::named_bar_sync(1 + g, 128);
-                    const float* bs = smem_fptr(sb);
-                    const float* ws = smem_fptr(sWsig);
-                    const float* wr = smem_fptr(sWrgb);
+                    const uint32_t tok = bar_sync_token(1 + g, 128);
+                    const float* bs = smem_fptr(sb, tok);
+                    const float* ws = smem_fptr(sWsig, tok);
+                    const float* wr = smem_fptr(sWrgb, tok);
                     if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
                     else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
                     else fwd_epilogue_layer<4, 2, false, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);

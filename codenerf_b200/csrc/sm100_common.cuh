@@ -19,7 +19,9 @@ constexpr int kNumStages = 4;
 constexpr int kABlock = 16384;          // activation K-block [128 rows x 64] bf16, 128-B swizzle
 constexpr int kDirBlock = 8192;         // PE(viewdir) block [128 rows x 32] bf16, 64-B swizzle
 constexpr int kATile = 4 * kABlock + kDirBlock;
-constexpr int kThreads = 320;           // warp 0 producer, warp 1 MMA, warps 2-5 group X, 6-9 group Y
+constexpr int kThreads = 384;           // warpgroup 0: producer, MMA issuer, 2 auxiliary warps; warps 4-7 group X, 8-11 group Y
+constexpr int kRegsAux = 64;            // setmaxnreg budgets: the pipeline warps give registers to the epilogue warps,
+constexpr int kRegsCompute = 216;       // which keep four 32-column TMEM loads in flight (384*168 >= 128*64 + 256*216)
 constexpr int kMaxLayers = 2 * CNB_MAX_BLOCKS + 4;
 
 // ---- optional cycle accounting of the pipeline roles (build with -DCNB_TRACE; debugging only) ----------
@@ -80,8 +82,9 @@ __device__ __forceinline__ uint32_t cvt_bf16x2(uint64_t v) {
 }
 template <int kOff>
 __device__ __forceinline__ void st_shared_v4_off(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0 + %5], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "n"(kOff)
-                 : "memory");
+    // volatile keeps it ordered against the fences / barrier arrivals (all volatile); no memory clobber, so ordinary
+    // loads (bias rows, head weights) can be scheduled across the operand stores
+    asm volatile("st.shared.v4.b32 [%0 + %5], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "n"(kOff));
 }
 
 // Vector load of 4 floats that every lane reads from the same address (bias / head-weight rows).  SM = true: `p`
@@ -91,15 +94,26 @@ __device__ __forceinline__ void st_shared_v4_off(uint32_t addr, uint32_t a, uint
 template <bool SM>
 __device__ __forceinline__ float4 ld_vec4(const float* p) {
     if (SM) {
+        // not volatile, no memory clobber: the scheduler may hoist these well ahead of their use (the address carries
+        // a data dependence on the barrier that published the staging buffer, see bar_sync_token)
         float4 v;
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                     : "r"((uint32_t)(uintptr_t)p));
+        asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+            : "r"((uint32_t)(uintptr_t)p));
         return v;
     }
     return __ldg(reinterpret_cast<const float4*>(p));
 }
-__device__ __forceinline__ const float* smem_fptr(const void* shared_ptr) {
-    return reinterpret_cast<const float*>((uintptr_t)umma::smem_u32(shared_ptr));
+__device__ __forceinline__ const float* smem_fptr(const void* shared_ptr, uint32_t token = 0u) {
+    return reinterpret_cast<const float*>((uintptr_t)(umma::smem_u32(shared_ptr) + token));
+}
+// 0 in a register the compiler cannot see through, defined after every earlier volatile asm (barriers included).
+__device__ __forceinline__ uint32_t order_token() { uint32_t t; asm volatile("mov.u32 %0, 0;" : "=r"(t) :: "memory"); return t; }
+// Named barrier that also returns 0 in a register defined by the barrier instruction itself: adding it to a
+// shared-memory address orders (non-volatile) loads from that address after the barrier.
+__device__ __forceinline__ uint32_t bar_sync_token(uint32_t id, uint32_t threads) {
+    uint32_t tok;
+    asm volatile("bar.sync %1, %2;\n\tmov.u32 %0, 0;" : "=r"(tok) : "r"(id), "r"(threads) : "memory");
+    return tok;
 }
 
 // Accumulators of the narrow heads carried across a layer's epilogue as packed pairs.
@@ -113,7 +127,8 @@ struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 template <int CC, int KIND, bool STORE, bool MASK, bool SM = false>
 __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const float* __restrict__ bias,
                                                const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
-                                               const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
+                                               const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr,
+                                               bool do_store = true) {
     constexpr bool RELU = (KIND != 1);
     uint32_t sgn = 0u;
 #pragma unroll
@@ -155,7 +170,7 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
                 a = ffma2(h[2], pk2f(w1.x, w1.y), a); a = ffma2(h[3], pk2f(w1.z, w1.w), a);
             }
         }
-        if (STORE) {
+        if (STORE && do_store) {
             constexpr int blk = CC >> 1;
             const int chunk = ((CC & 1) << 2) + j8;
             st_shared_v4_off<blk * kABlock>(a8[chunk], cvt_bf16x2<RELU>(v[0]), cvt_bf16x2<RELU>(v[1]),
@@ -165,25 +180,57 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
     if (MASK && RELU) umma::st_global_hint(mscr + (size_t)CC * kTileRows, ~sgn, acc.mask_policy);   // bit set <=> pre-activation >= +0
 }
 
-// A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.
+// A whole layer: NCC x 32 columns.  tcgen05.ld is latency bound (~300 cycles per 32x32 load, tests/probe_ts.cu),
+// so four loads are in flight at the start and the next two are issued before the previous two are consumed.
 template <int NCC, int KIND, bool STORE, bool MASK, bool SM = false>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                    const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
-    auto pair = [&](auto cc_tag) {
-        constexpr int CC = decltype(cc_tag)::value;
-        uint32_t ra[32], rb[32];
-        umma::tmem_ld32(taddr + CC * 32, ra);
-        umma::tmem_ld32(taddr + CC * 32 + 32, rb);
-        umma::tmem_ld_wait();
-        fwd_epilogue32<CC, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
-    };
-    pair(std::integral_constant<int, 0>{});
-    pair(std::integral_constant<int, 2>{});
+    uint32_t ra[32], rb[32], rc[32], rd[32];
+    umma::tmem_ld32(taddr + 0, ra);
+    umma::tmem_ld32(taddr + 32, rb);
+    umma::tmem_ld32(taddr + 64, rc);
+    umma::tmem_ld32(taddr + 96, rd);
+    umma::tmem_ld_wait();
+    fwd_epilogue32<0, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    fwd_epilogue32<1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
     if constexpr (NCC == 8) {
-        pair(std::integral_constant<int, 4>{});
-        pair(std::integral_constant<int, 6>{});
+        umma::tmem_ld32(taddr + 128, ra);
+        umma::tmem_ld32(taddr + 160, rb);
+    }
+    fwd_epilogue32<2, KIND, STORE, MASK, SM>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    fwd_epilogue32<3, KIND, STORE, MASK, SM>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    if constexpr (NCC == 8) {
+        umma::tmem_ld32(taddr + 192, rc);
+        umma::tmem_ld32(taddr + 224, rd);
+        umma::tmem_ld_wait();
+        fwd_epilogue32<4, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<5, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<6, KIND, STORE, MASK, SM>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<7, KIND, STORE, MASK, SM>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    }
+}
+
+// NC (2 or 4) consecutive 32-column chunks of a layer: one thread's share when two warps split the columns of a row.
+// Every pointer / address argument is pre-offset to the thread's first chunk (so the column half is a run-time
+// value and the code exists once); a8 must point at the K-block that holds the first chunk.
+template <int NC, int KIND, bool MASK, bool SM>
+__device__ __forceinline__ void fwd_epilogue_chunks(uint32_t taddr, const float* __restrict__ bias, const uint32_t (&a8)[8],
+                                                    const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
+                                                    HeadAcc& acc, uint32_t* mscr, bool do_store) {
+    // two loads in flight per warp: the second warp of the scheduler (the other column half) hides their latency
+    uint32_t ra[32], rb[32];
+    umma::tmem_ld32(taddr + 0, ra);
+    umma::tmem_ld32(taddr + 32, rb);
+    umma::tmem_ld_wait();
+    fwd_epilogue32<0, KIND, true, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
+    fwd_epilogue32<1, KIND, true, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
+    if constexpr (NC == 4) {
+        umma::tmem_ld32(taddr + 64, ra);
+        umma::tmem_ld32(taddr + 96, rb);
+        umma::tmem_ld_wait();
+        fwd_epilogue32<2, KIND, true, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
+        fwd_epilogue32<3, KIND, true, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
     }
 }
 

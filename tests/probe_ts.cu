@@ -10,7 +10,7 @@
 #include <cmath>
 #include <vector>
 #include <cuda_runtime.h>
-#include "../codenerf_b200/csrc/umma.cuh"
+#include "../codenerf_b200/csrc/sm100_common.cuh"
 
 namespace {
 constexpr int kSlot = 16384;
@@ -379,6 +379,66 @@ __global__ void __launch_bounds__(512, 1) k_ldtm(int iters, int per_wait, unsign
     if (warp == 0) umma::tmem_dealloc(tmem, 512);
 }
 
+// The forward epilogue of one 128 x 256 layer in isolation (no MMAs, no weight stream): `nwarps` = 4 (one tile) or 8
+// (two tiles at once).  WITH_MMA = 1 adds a warp that keeps the tensor pipe busy with SS MMAs on resident operands.
+template <int WITH_MMA>
+__global__ void __launch_bounds__(384, 1) k_epi(int layers, int nwarps, unsigned long long* cycles, const float* gbias) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;                      // 2 operand tiles
+    uint8_t* sW = smem + 2 * sm100::kATile;  // 4 stages (garbage is fine)
+    float* sBias = (float*)(sW + 4 * kSlot);
+    __shared__ uint32_t tmem_slot;
+    __shared__ uint64_t done;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { umma::mbar_init(&done, 1); umma::fence_mbar_init(); }
+    if (warp == 1) umma::tmem_alloc(&tmem_slot, 512);
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sBias[i] = gbias[i];
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    if (warp >= 4 && warp < 4 + nwarps) {
+        const int g = (warp - 4) >> 2, q = warp & 3, row = q * 32 + lane;
+        uint8_t* sAg = sA + g * sm100::kATile;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)g * 256u;
+        uint32_t a8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a8[c] = umma::smem_u32(sAg + row * 128 + ((c ^ (row & 7)) << 4));
+        sm100::HeadAcc acc = {0ull, 0ull, 0ull, 0ull, 0ull};
+        const float* bs = sm100::smem_fptr(sBias, sm100::order_token());
+        const long long t0 = clock64();
+        for (int l = 0; l < layers; ++l) {
+            sm100::fwd_epilogue_layer<8, 0, true, false, true>(taddr, bs, a8, bs, bs, acc, nullptr);
+            umma::tc_fence_before();
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+        }
+        const long long dt = clock64() - t0;
+        if (lane == 0) atomicMax(cycles, (unsigned long long)dt);
+    } else if (WITH_MMA && warp == 1) {
+        const uint64_t dA = umma::make_sdesc(umma::smem_u32(sA), 16, 1024, umma::SWZ_128B);
+        const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 1024, umma::SWZ_128B);
+        const uint32_t id256 = umma::make_idesc(128, 256, 0, 0);
+        // about as many layers' worth of MMAs as the epilogue loop will take (2048 cycles each)
+        for (int l = 0; l < layers; ++l) {
+            if (umma::elect_one()) {
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                        umma::mma_bf16(tmem + 256, dA + ((c * kSlot) >> 4) + ks * 2, dB + (((c & 1) * 2 * kSlot) >> 4) + ks * 2, id256, 1u);
+            }
+            __syncwarp();
+        }
+        if (umma::elect_one()) umma::mma_commit(&done);
+        __syncwarp();
+        umma::mbar_wait(&done, 0);
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
 template <int MODE, int FILL>
 void run_perf(const uint8_t* wimg, int n_slots, int layers, unsigned long long* d_cyc, const char* name) {
     const size_t smem = 1024 + (MODE == 0 ? 4 * kSlot : 0) + (size_t)n_slots * kSlot;
@@ -432,7 +492,7 @@ int main() {
     run_perf<1, 1>(wimg, 12, layers, d_cyc, "TS N=128, streamed");
     {
         uint32_t* sink; cudaMalloc(&sink, 4);
-        for (int nw : {4, 8, 16})
+        for (int nw : {4, 8})
             for (int pw : {1, 2, 4}) {
                 const int iters = 4096;
                 cudaMemset(d_cyc, 0, 8);
@@ -441,6 +501,23 @@ int main() {
                 unsigned long long c = 0; cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost);
                 printf("TS_PROBE ldtm warps=%2d loads/wait=%d: %6.1f B/clk/SM (%5.1f clk per 4 KB load per warp)  err=%s\n", nw, pw,
                        (double)nw * iters * 4096.0 / (double)c, (double)c / iters, cudaGetErrorName(e2));
+            }
+    }
+    {
+        float* gb; cudaMalloc(&gb, 1024); cudaMemset(gb, 0, 1024);
+        const size_t esm = 1024 + 2 * sm100::kATile + 4 * kSlot + 1024;
+        cudaFuncSetAttribute(k_epi<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm);
+        cudaFuncSetAttribute(k_epi<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)esm);
+        for (int with_mma = 0; with_mma < 2; ++with_mma)
+            for (int nw : {4, 8}) {
+                if (with_mma && nw == 8) continue;       // the MMA warp accumulates into tile 1's columns
+                for (int rep = 0; rep < 2; ++rep) {
+                    cudaMemset(d_cyc, 0, 8);
+                    if (with_mma) k_epi<1><<<148, 384, esm>>>(2000, nw, d_cyc, gb); else k_epi<0><<<148, 384, esm>>>(2000, nw, d_cyc, gb);
+                    cudaError_t e2 = cudaDeviceSynchronize();
+                    unsigned long long c = 0; cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost);
+                    if (rep) printf("TS_PROBE epilogue warps=%d mma=%d: %7.1f cycles per 128x256 layer per tile  err=%s\n", nw, with_mma, (double)c / 2000.0, cudaGetErrorName(e2));
+                }
             }
     }
     run_shared<1>(wimg, 10, layers / 2, d_cyc, "TS N=128, X+Y share a pass");
