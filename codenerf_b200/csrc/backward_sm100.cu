@@ -898,7 +898,8 @@ __global__ void k_l2_seed_sm100(const float* __restrict__ rgb, const float* __re
 // ===========================================================================
 // Host side
 
-constexpr int64_t kMaxSubTiles = 8192;     // rows per sub-batch = 1 Mi (stash ~ 8 GB)
+// rows per sub-batch = 128 x this: 8192 tiles = 1 Mi rows (stash ~ 8 GB); CNB_SUB_TILES overrides (experiments)
+static const int64_t kMaxSubTiles = [] { const char* e = getenv("CNB_SUB_TILES"); const long v = e ? atol(e) : 0; return (int64_t)(v >= 256 ? v : 8192); }();
 
 struct StashLayout {
     uint32_t a_slot[kMaxLayers + 1], dir_slot, d_slot[kMaxLayers], a_tile_bytes, d_tile_bytes;
@@ -923,11 +924,16 @@ struct BwdWorkspace {
     uint32_t* masks;
     float *spill_sig, *spill_rgb, *dsig, *drgb, *dspre, *ray_drgb, *ray_rgb, *ray_depth, *ray_acc;
     uint8_t *stashA, *stashD;
+    // second copy of everything K2 hands to K3 (stash, dspre, per-sample d rgb): with more than one sub-batch K3 of
+    // sub-batch i runs on a second stream while K2 of sub-batch i + 1 fills the other copy
+    uint8_t *stashA2, *stashD2;
+    float *dspre2, *drgb2;
+    int nbuf;
     size_t bytes;
 };
 
 size_t carve_bwd(const cnb_net_config* c, const Plan& pl, int n_codes, int64_t sub_rows, int64_t sub_rays, int fused,
-                 int stash, int grid, char* base, BwdWorkspace* out) {
+                 int stash, int grid, char* base, BwdWorkspace* out, int nbuf = 1) {
     size_t off = 0;
     auto take = [&](size_t bytes) -> char* { char* p = base ? base + off : nullptr; off += (bytes + 1023) & ~(size_t)1023; return p; };
     BwdWorkspace w = {};
@@ -953,7 +959,14 @@ size_t carve_bwd(const cnb_net_config* c, const Plan& pl, int n_codes, int64_t s
         const int64_t tiles = (sub_rows + kTileRows - 1) / kTileRows;
         w.stashA = (uint8_t*)take((size_t)tiles * sl.a_tile_bytes);
         w.stashD = (uint8_t*)take((size_t)tiles * sl.d_tile_bytes);
+        if (nbuf > 1) {
+            w.stashA2 = (uint8_t*)take((size_t)tiles * sl.a_tile_bytes);
+            w.stashD2 = (uint8_t*)take((size_t)tiles * sl.d_tile_bytes);
+            w.dspre2 = (float*)take(sizeof(float) * (size_t)sub_rows);
+            w.drgb2 = (float*)take(sizeof(float) * (size_t)sub_rows * 3);
+        }
     }
+    w.nbuf = nbuf;
     w.bytes = off;
     if (out) *out = w;
     return off;
@@ -963,6 +976,50 @@ int num_sms() {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     return sms;
+}
+
+// K2 -> K3 software pipeline across sub-batches.  K2 is bound by on-chip latencies and K3 by HBM, so they overlap
+// well: K3 (+ the head-gradient kernel) of sub-batch i runs on a helper stream on `k3_sms` SMs while K2 of
+// sub-batch i + 1 runs on the remaining SMs (neither kernel can share an SM with the other: shared memory).
+struct Pipeline {
+    bool on = false;
+    cudaStream_t st3 = nullptr;
+    cudaEvent_t k2_done[2] = {nullptr, nullptr}, k3_done[2] = {nullptr, nullptr};
+    bool pending[2] = {false, false};      // a K3 of this buffer is in flight on st3
+    int k3_sms = 0;
+};
+struct PipelineResources { cudaStream_t st3; cudaEvent_t ev[4]; bool ok; };
+PipelineResources* pipeline_resources() {
+    static thread_local PipelineResources res[16] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    PipelineResources& r = res[dev];
+    if (!r.ok) {
+        if (cudaStreamCreateWithFlags(&r.st3, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        for (int i = 0; i < 4; ++i)
+            if (cudaEventCreateWithFlags(&r.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        r.ok = true;
+    }
+    return &r;
+}
+int pipeline_begin(Pipeline& pp, int64_t n_sub, bool training) {
+    static const int want = [] { const char* e = getenv("CNB_K3_OVERLAP"); return e ? atoi(e) : 0; }();   // measured: no gain
+    static const int k3_sms = [] { const char* e = getenv("CNB_K3_SMS"); return e ? atoi(e) : 40; }();
+    pp = Pipeline();
+    if (!want || !training || n_sub < 2) return CNB_OK;
+    PipelineResources* r = pipeline_resources();
+    if (!r) return CNB_E_DEVICE;
+    pp.on = true; pp.st3 = r->st3;
+    pp.k2_done[0] = r->ev[0]; pp.k2_done[1] = r->ev[1]; pp.k3_done[0] = r->ev[2]; pp.k3_done[1] = r->ev[3];
+    pp.k3_sms = k3_sms;
+    return CNB_OK;
+}
+// join: everything queued on the helper stream is ordered before what follows on `st`
+int pipeline_end(Pipeline& pp, cudaStream_t st) {
+    if (!pp.on) return CNB_OK;
+    for (int b = 0; b < 2; ++b)
+        if (pp.pending[b]) { CNB_CUDA_TRY(cudaStreamWaitEvent(st, pp.k3_done[b], 0)); pp.pending[b] = false; }
+    return CNB_OK;
 }
 
 // K2 (+ K3 and head gradients when d_params != null) over launch-relative rows [0, S).
@@ -976,7 +1033,15 @@ struct FuseArgs {     // compositing (+ loss) fused into K2: per-ray arrays are 
 int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* packed, const Plan& pl, BwdWorkspace& w,
                 int mode, const CnbRaySource* rs, const float* xyz, const float* viewdir, int64_t S, int64_t row_offset,
                 int n_codes, int64_t rows_per_code, const float* d_sigmas, const float* d_rgbs, float* d_params,
-                cudaStream_t st, const FuseArgs* fuse = nullptr) {
+                cudaStream_t st, const FuseArgs* fuse = nullptr, Pipeline* pp = nullptr, int sub_index = 0,
+                bool last_sub = true) {
+    // which copy of the K2 -> K3 hand-over buffers this sub-batch uses
+    const int buf = (pp && pp->on && w.nbuf > 1) ? (sub_index & 1) : 0;
+    uint8_t* stashA = buf ? w.stashA2 : w.stashA;
+    uint8_t* stashD = buf ? w.stashD2 : w.stashD;
+    float* dspre_buf = buf ? w.dspre2 : w.dspre;
+    float* drgb_buf = buf ? w.drgb2 : w.drgb;
+    const bool piped = pp && pp->on && w.nbuf > 1;
     CnbLayout L; cnb_make_layout(c, &L);
     const StashLayout sl = make_stash_layout(pl);
     BwdParams bp = {};
@@ -1003,7 +1068,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.xyz = xyz; bp.viewdir = viewdir; bp.S = S; bp.row_offset = row_offset;
     bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
     bp.mask_scratch = w.masks; bp.colsum = w.colsum;
-    bp.stash = d_params ? 1 : 0; bp.stashA = w.stashA; bp.stashD = w.stashD; bp.dspre = w.dspre;
+    bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux
     // warps of K2 do it, and only for the folded layers (the latent-code gradients need nothing else)
     bp.colsum_layers = 0u;
@@ -1014,8 +1079,8 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         bp.fuse_comp = fuse->kind; bp.white_bg = fuse->white_bg; bp.n_rays_total = fuse->n_rays_total;
         bp.d_rgb_rays = fuse->d_rgb; bp.d_depth_rays = fuse->d_depth; bp.target = fuse->target; bp.loss_scale = fuse->loss_scale;
         bp.out_rgb = fuse->rgb; bp.out_depth = fuse->depth; bp.out_acc = fuse->acc; bp.sq_err = fuse->sq_err;
-        bp.drgb_out = w.drgb;
-        d_rgbs = w.drgb;          // the head weight gradient reads the per-sample seeds K2 writes
+        bp.drgb_out = drgb_buf;
+        d_rgbs = drgb_buf;        // the head weight gradient reads the per-sample seeds K2 writes
     }
     for (int l = 0; l <= nl; ++l) bp.a_slot[l] = sl.a_slot[l];
     for (int l = 0; l < nl; ++l) bp.d_slot[l] = sl.d_slot[l];
@@ -1025,6 +1090,12 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     const int64_t tiles = (S + kTileRows - 1) / kTileRows;
     const int64_t units = (tiles + 1) / 2;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
+    // pipelined: leave SMs to the K3 of the previous sub-batch (the first K2 has the GPU to itself)
+    if (piped && sub_index > 0 && grid > sms - pp->k3_sms && sms > pp->k3_sms) grid = sms - pp->k3_sms;
+    if (piped && pp->pending[buf]) {      // the K3 that read this copy two sub-batches ago must be done
+        CNB_CUDA_TRY(cudaStreamWaitEvent(st, pp->k3_done[buf], 0));
+        pp->pending[buf] = false;
+    }
     const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256 + 4 * kTileRows * sizeof(float4) +
                         sizeof(float) * (4 * kW + kW + 3 * (kW / 2));
     const int mc = grid == sms ? weight_multicast() : 1;
@@ -1045,7 +1116,13 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     CNB_LAUNCH_CHECK();
     if (!d_params) return CNB_OK;
 
-    // ---- K3: weight gradients ----
+    // ---- K3: weight gradients (on the helper stream when pipelined) ----
+    cudaStream_t st2 = st;
+    if (piped) {
+        CNB_CUDA_TRY(cudaEventRecord(pp->k2_done[buf], st));
+        CNB_CUDA_TRY(cudaStreamWaitEvent(pp->st3, pp->k2_done[buf], 0));
+        st2 = pp->st3;
+    }
     WgParams wp = {};
     int np = 0;
     auto add = [&](int lay, int64_t w_off, int ld, int col0, int n_valid, int n_blocks, uint32_t a_off, int is_dir) {
@@ -1079,23 +1156,28 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         wp.prob[i].splits = (int32_t)sp; wp.prob[i].item0 = items; items += (int)sp;
     }
     wp.n_problems = np; wp.n_items = items;
-    wp.stashA = w.stashA; wp.stashD = w.stashD; wp.a_tile_bytes = sl.a_tile_bytes; wp.d_tile_bytes = sl.d_tile_bytes;
+    wp.stashA = stashA; wp.stashD = stashD; wp.a_tile_bytes = sl.a_tile_bytes; wp.d_tile_bytes = sl.d_tile_bytes;
     wp.n_tiles = tiles; wp.dP = d_params;
     wp.colsum = w.colsum; wp.n_layers = nl; wp.n_codes = n_codes; wp.rows_per_code = rows_per_code; wp.row_offset = row_offset;
     const size_t wsmem = 1024 + (size_t)kWgStages * kWgStage + 256;
     CNB_CUDA_TRY(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
-    const int wgrid = items < sms ? items : sms;
-    cnb_prof_begin(CNB_K_WGRAD, st);
-    k_wgrad<<<wgrid, kWgThreads, wsmem, st>>>(wp);
-    cnb_prof_end(CNB_K_WGRAD, st);
+    int wgrid = items < sms ? items : sms;
+    if (piped && !last_sub && wgrid > pp->k3_sms) wgrid = pp->k3_sms;      // the last K3 overlaps nothing: whole GPU
+    cnb_prof_begin(CNB_K_WGRAD, st2);
+    k_wgrad<<<wgrid, kWgThreads, wsmem, st2>>>(wp);
+    cnb_prof_end(CNB_K_WGRAD, st2);
     CNB_LAUNCH_CHECK();
     // narrow heads (sigma, rgb.2): inputs f (input of encoding_viewdir) and the rgb.0 hidden
     int l_vd = 1 + c->shape_blocks + 1;
     const int hgrid = (int)(tiles < 6 * sms ? tiles : 6 * sms);
-    k_head_wgrad<<<hgrid, 256, 0, st>>>(w.stashA, sl.a_tile_bytes, sl.a_slot[l_vd], sl.a_slot[nl], w.dspre, d_rgbs, S, tiles,
-                                       d_params + L.sigma_w, d_params + L.sigma_b, d_params + L.rgb2_w,
-                                       d_params + L.rgb2_b);
+    k_head_wgrad<<<hgrid, 256, 0, st2>>>(stashA, sl.a_tile_bytes, sl.a_slot[l_vd], sl.a_slot[nl], dspre_buf, d_rgbs, S, tiles,
+                                        d_params + L.sigma_w, d_params + L.sigma_b, d_params + L.rgb2_w,
+                                        d_params + L.rgb2_b);
     CNB_LAUNCH_CHECK();
+    if (piped) {
+        CNB_CUDA_TRY(cudaEventRecord(pp->k3_done[buf], pp->st3));
+        pp->pending[buf] = true;
+    }
     return CNB_OK;
 }
 
@@ -1152,7 +1234,7 @@ size_t bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int64_t n_rays,
     int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
     int64_t sub_rays = fused ? (sub_rows / N < 1 ? 1 : sub_rows / N) : 0;
     if (fused) { if (sub_rays > n_rays) sub_rays = n_rays; sub_rows = sub_rays * N; }
-    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, 148 * 2, nullptr, nullptr) + 1024;
+    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, 148 * 2, nullptr, nullptr, S > sub_rows ? 2 : 1) + 1024;
 }
 
 // Fused render backward (mode 1: seeds given; mode 2: L2 loss against target).
@@ -1179,18 +1261,28 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
     if ((kTileRows % N) == 0 && sub_rays < rays->n_rays) sub_rays -= sub_rays % (kTileRows / N);
     sub_rows = sub_rays * N;
     BwdWorkspace w;
-    const size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr);
+    const int64_t n_sub = (rays->n_rays + sub_rays - 1) / sub_rays;
+    int nbuf = n_sub > 1 ? 2 : 1;
+    size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr, nbuf);
+    if (nbuf > 1 && ws && ws_bytes < need) {     // a caller-sized workspace without the second hand-over copy: no overlap
+        nbuf = 1;
+        need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr, nbuf);
+    }
     if (!ws || ws_bytes < need) return CNB_E_WORKSPACE;
     if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
-    carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, (char*)ws, &w);
+    carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, (char*)ws, &w, nbuf);
+    Pipeline pipe;
+    CNB_TRY(pipeline_begin(pipe, n_sub, d_params != nullptr));
     CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w.fw, st));
     CNB_CUDA_TRY(cudaMemsetAsync(w.colsum, 0, sizeof(float) * (size_t)rays->n_codes * pl.n_layers * kW, st));
     if (mode == 2 && sq_err)
         CNB_CUDA_TRY(cudaMemsetAsync(sq_err, 0, sizeof(float) * (size_t)(rays->n_rays / rays->rays_per_segment), st));
     CnbRaySource rs = cnb_make_ray_source(rays);
     const bool fuse = (kTileRows % N) == 0 && (sub_rays * N) % kTileRows == 0;
-    for (int64_t r0 = 0; r0 < rays->n_rays; r0 += sub_rays) {
+    int sub = 0;
+    for (int64_t r0 = 0; r0 < rays->n_rays; r0 += sub_rays, ++sub) {
         const int64_t nr = rays->n_rays - r0 < sub_rays ? rays->n_rays - r0 : sub_rays;
+        const bool last_sub = r0 + sub_rays >= rays->n_rays;
         if (fuse) {
             // every 128-row tile holds whole rays: compositing, the loss seed and its backward run inside K2
             FuseArgs fa = {};
@@ -1198,7 +1290,7 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
             fa.d_rgb = d_rgb; fa.d_depth = d_depth; fa.target = target; fa.loss_scale = loss_scale;
             fa.rgb = rgb; fa.depth = depth; fa.acc = acc; fa.sq_err = mode == 2 ? sq_err : nullptr;
             CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 0, &rs, nullptr, nullptr, nr * N, r0 * N, rays->n_codes,
-                                rays->n_codes > 1 ? rows_per_code : S, nullptr, nullptr, d_params, st, &fa));
+                                rays->n_codes > 1 ? rows_per_code : S, nullptr, nullptr, d_params, st, &fa, &pipe, sub, last_sub));
             continue;
         }
         // general N: forward kernel (spilling per-sample sigma / rgb), compositing backward, then K2
@@ -1217,12 +1309,19 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
             seed_rgb = d_rgb + r0 * 3;
             seed_depth = d_depth ? d_depth + r0 : nullptr;
         }
+        // the per-sample d rgb is also read by the head-gradient kernel that runs with K3: it lives in the hand-over copy
+        float* drgb_sub = (pipe.on && w.nbuf > 1 && (sub & 1)) ? w.drgb2 : w.drgb;
+        if (pipe.on && w.nbuf > 1 && pipe.pending[sub & 1]) {
+            CNB_CUDA_TRY(cudaStreamWaitEvent(st, pipe.k3_done[sub & 1], 0));
+            pipe.pending[sub & 1] = false;
+        }
         CNB_TRY(cnb_vr_backward_segments(w.spill_sig, w.spill_rgb, rays->z_vals, rays->z_per_segment,
                                          rays->rays_per_segment, r0, nr, N, rays->white_bg, seed_rgb, seed_depth, w.dsig,
-                                         w.drgb, st));
+                                         drgb_sub, st));
         CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 0, &rs, nullptr, nullptr, nr * N, r0 * N, rays->n_codes,
-                            rays->n_codes > 1 ? rows_per_code : S, w.dsig, w.drgb, d_params, st));
+                            rays->n_codes > 1 ? rows_per_code : S, w.dsig, drgb_sub, d_params, st, nullptr, &pipe, sub, last_sub));
     }
+    CNB_TRY(pipeline_end(pipe, st));
     return finish_bwd(cfg, P, pl, w, rays->shape_codes, rays->texture_codes, rays->n_codes, d_params, d_shape, d_tex, st);
 }
 
@@ -1237,17 +1336,28 @@ int cnb_sm100_mlp_backward(const cnb_net_config* cfg, const float* const* P, con
     if (n_codes > 1 && (samples_per_code % kTileRows) != 0) return CNB_E_UNSUPPORTED;
     const int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
     BwdWorkspace w;
-    const size_t need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr);
+    const int64_t n_sub = sub_rows > 0 ? (S + sub_rows - 1) / sub_rows : 1;
+    int nbuf = n_sub > 1 ? 2 : 1;
+    size_t need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr, nbuf);
+    if (nbuf > 1 && ws && ws_bytes < need) {
+        nbuf = 1;
+        need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr, nbuf);
+    }
     if (!ws || ws_bytes < need) return CNB_E_WORKSPACE;
     if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
-    carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, (char*)ws, &w);
+    carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, (char*)ws, &w, nbuf);
+    Pipeline pipe;
+    CNB_TRY(pipeline_begin(pipe, n_sub, d_params != nullptr));
     CNB_TRY(latent_and_fold(cfg, P, shape_codes, tex_codes, n_codes, w.fw, st));
     CNB_CUDA_TRY(cudaMemsetAsync(w.colsum, 0, sizeof(float) * (size_t)n_codes * pl.n_layers * kW, st));
-    for (int64_t r0 = 0; r0 < S; r0 += sub_rows) {
+    int sub = 0;
+    for (int64_t r0 = 0; r0 < S; r0 += sub_rows, ++sub) {
         const int64_t m = S - r0 < sub_rows ? S - r0 : sub_rows;
         CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 1, nullptr, xyz + r0 * 3, viewdir + r0 * 3, m, r0, n_codes,
-                            n_codes > 1 ? samples_per_code : S, d_sigmas + r0, d_rgbs + r0 * 3, d_params, st));
+                            n_codes > 1 ? samples_per_code : S, d_sigmas + r0, d_rgbs + r0 * 3, d_params, st, nullptr, &pipe,
+                            sub, r0 + sub_rows >= S));
     }
+    CNB_TRY(pipeline_end(pipe, st));
     return finish_bwd(cfg, P, pl, w, shape_codes, tex_codes, n_codes, d_params, d_shape, d_tex, st);
 }
 
