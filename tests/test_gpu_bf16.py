@@ -1,5 +1,7 @@
 """bf16 tensor-core path (tcgen05 / TMEM kernels) against the oracle.
 Tolerance: rgb / depth / acc within 1e-2 absolute (BASELINE.json north_star, bf16 mode)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -50,7 +52,7 @@ def test_unfused_forward_bf16_vs_reference_fixture(c):
     np.testing.assert_allclose(acc.cpu().numpy(), G_REN[f"r{k}_acc"], atol=ATOL, rtol=0)
 
 
-def _fused_case(N, H, W, n_seg, ray_count, cat, explicit_rays=False, n_codes=None):
+def _fused_case(N, H, W, n_seg, ray_count, cat, explicit_rays=False, n_codes=None, with_ref=True):
     import codenerf_b200 as cn
     model, flat = U.make_model("bf16")
     focal = 131.25 * W / 128.0
@@ -62,7 +64,7 @@ def _fused_case(N, H, W, n_seg, ray_count, cat, explicit_rays=False, n_codes=Non
     code_of = (lambda g: g) if nc == n_seg else (lambda g: 0)
     ref = [orc.render(flat, H, W, focal, c2ws[g], zs[g], scodes[code_of(g):code_of(g) + 1],
                       tcodes[code_of(g):code_of(g) + 1], True, ray_begin=int(pix[g]), ray_count=ray_count)
-           for g in range(n_seg)]
+           for g in range(n_seg)] if with_ref else None
     if explicit_rays:
         ros, vds = [], []
         for g in range(n_seg):
@@ -87,6 +89,7 @@ def _fused_case(N, H, W, n_seg, ray_count, cat, explicit_rays=False, n_codes=Non
     (40, 16, 16, 1, 77, syn.SRN_CARS, True),           # ragged everything, rays from memory
     (128, 16, 16, 4, 16, syn.SRN_CHAIRS, True),
     (200, 16, 16, 1, 7, syn.SRN_CARS, False),          # a ray longer than a tile
+    (400, 16, 16, 2, 6, syn.SRN_CARS, False),          # very long rays: no room to stage bias rows in shared memory
 ])
 def test_fused_forward_bf16_vs_oracle(N, H, W, n_seg, ray_count, cat, explicit):
     import codenerf_b200 as cn
@@ -103,6 +106,31 @@ def test_fused_forward_bf16_vs_oracle(N, H, W, n_seg, ray_count, cat, explicit):
     np.testing.assert_allclose(rgb.cpu().numpy(), rgb_ref, atol=ATOL, rtol=0)
     np.testing.assert_allclose(depth.cpu().numpy(), d_ref, atol=ATOL, rtol=0)
     np.testing.assert_allclose(acc.cpu().numpy(), a_ref, atol=ATOL, rtol=0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"CNB_FWD_KERNEL": "ts"}, {"CNB_CTA_PAIRS": "1"}, {"CNB_WEIGHT_MCAST": "2"}],
+                         ids=["tmem-operands", "cta-pairs", "multicast2"])
+def test_forward_kernel_variants_match_default(env):
+    """The opt-in forward kernels (measured, not faster) compute the same image as the default:
+    full-grid problem (the variants only engage when every SM has work), compared with the default kernel."""
+    import codenerf_b200 as cn
+    model, flat, bundle, scodes, tcodes, zs, ref = _fused_case(64, 128, 128, 24, 2048, syn.SRN_CARS, False, with_ref=False)
+    sc, tc = torch.from_numpy(scodes).cuda(), torch.from_numpy(tcodes).cuda()
+    with torch.no_grad():
+        base = [t.clone() for t in cn.render(model, bundle, sc, tc)]
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            got = cn.render(model, bundle, sc, tc)
+            torch.cuda.synchronize()
+        finally:
+            for k, v in old.items():
+                if v is None: os.environ.pop(k, None)
+                else: os.environ[k] = v
+    _no_timeouts()
+    for a, b in zip(got, base):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), atol=2e-3, rtol=0)
 
 
 @pytest.mark.gpu
