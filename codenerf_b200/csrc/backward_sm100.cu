@@ -1002,8 +1002,12 @@ PipelineResources* pipeline_resources() {
     }
     return &r;
 }
-int pipeline_begin(Pipeline& pp, int64_t n_sub, bool training) {
+bool pipeline_wanted() {
     static const int want = [] { const char* e = getenv("CNB_K3_OVERLAP"); return e ? atoi(e) : 0; }();   // measured: no gain
+    return want != 0;
+}
+int pipeline_begin(Pipeline& pp, int64_t n_sub, bool training) {
+    const bool want = pipeline_wanted();
     static const int k3_sms = [] { const char* e = getenv("CNB_K3_SMS"); return e ? atoi(e) : 40; }();
     pp = Pipeline();
     if (!want || !training || n_sub < 2) return CNB_OK;
@@ -1234,7 +1238,7 @@ size_t bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int64_t n_rays,
     int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
     int64_t sub_rays = fused ? (sub_rows / N < 1 ? 1 : sub_rows / N) : 0;
     if (fused) { if (sub_rays > n_rays) sub_rays = n_rays; sub_rows = sub_rays * N; }
-    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, 148 * 2, nullptr, nullptr, S > sub_rows ? 2 : 1) + 1024;
+    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, 148 * 2, nullptr, nullptr, (pipeline_wanted() && S > sub_rows) ? 2 : 1) + 1024;
 }
 
 // Fused render backward (mode 1: seeds given; mode 2: L2 loss against target).
@@ -1262,7 +1266,7 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
     sub_rows = sub_rays * N;
     BwdWorkspace w;
     const int64_t n_sub = (rays->n_rays + sub_rays - 1) / sub_rays;
-    int nbuf = n_sub > 1 ? 2 : 1;
+    int nbuf = (pipeline_wanted() && n_sub > 1) ? 2 : 1;
     size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr, nbuf);
     if (nbuf > 1 && ws && ws_bytes < need) {     // a caller-sized workspace without the second hand-over copy: no overlap
         nbuf = 1;
@@ -1337,7 +1341,7 @@ int cnb_sm100_mlp_backward(const cnb_net_config* cfg, const float* const* P, con
     const int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
     BwdWorkspace w;
     const int64_t n_sub = sub_rows > 0 ? (S + sub_rows - 1) / sub_rows : 1;
-    int nbuf = n_sub > 1 ? 2 : 1;
+    int nbuf = (pipeline_wanted() && n_sub > 1) ? 2 : 1;
     size_t need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr, nbuf);
     if (nbuf > 1 && ws && ws_bytes < need) {
         nbuf = 1;
