@@ -421,20 +421,17 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             ++wp;
         };
 
-        for (int r = 0; r < rounds; ++r) {
-            const int t = 2 * r + g;
-            if (t >= T) break;
-            const bool phantom = t >= T_own;
-            const long long tr_e0 = CNB_TR_NOW();
-            const int64_t lrow = (tile0 + t) * kTileRows + row;      // launch-relative row
-            const bool valid = !phantom && lrow < p.S;
-            const int64_t grow = p.row_offset + lrow;                // global row
+        // rays / samples / positional encodings of tile slot t of this group, as packed bf16 rows in registers
+        auto prepare_tile = [&](int t, PeRow& pe) {
+            const bool ph = t >= T_own;
+            const int64_t lr = (tile0 + t) * kTileRows + row;
+            const bool ok = !ph && t < T && lr < p.S;
             float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-            float ds = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
-            if (valid) {
+            if (ok) {
                 if (p.mode == 0) {
-                    const int64_t ray = grow / N;
-                    const int zi = (int)(grow - ray * N);
+                    const int64_t gr = p.row_offset + lr;
+                    const int64_t ray = gr / N;
+                    const int zi = (int)(gr - ray * N);
                     float o[3];
                     cnb_fetch_ray(p.rs, ray, o, dir);
                     const int64_t seg = ray / p.rs.rays_per_segment;
@@ -443,19 +440,34 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + lrow * 3 + k); dir[k] = __ldg(p.viewdir + lrow * 3 + k); }
+                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + lr * 3 + k); dir[k] = __ldg(p.viewdir + lr * 3 + k); }
                 }
-                if (!p.fuse_comp) {
-                    ds = __ldg(p.d_sigmas + lrow);
-                    dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
-                }
+            }
+            pe_compute_xyz(pos, ok, pe.x);
+            pe_compute_dir(dir, ok, pe.d);
+        };
+        PeRow pe;
+        if (g < T) prepare_tile(g, pe);
+
+        for (int r = 0; r < rounds; ++r) {
+            const int t = 2 * r + g;
+            if (t >= T) break;
+            const bool phantom = t >= T_own;
+            const long long tr_e0 = CNB_TR_NOW();
+            const int64_t lrow = (tile0 + t) * kTileRows + row;      // launch-relative row
+            const bool valid = !phantom && lrow < p.S;
+            float ds = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
+            if (valid && !p.fuse_comp) {
+                ds = __ldg(p.d_sigmas + lrow);
+                dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
             }
             int64_t code = 0;
             if (p.n_codes > 1) { code = (p.row_offset + (tile0 + t) * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
 
-            // ---- phase F0: positional encodings ----
+            // ---- phase F0: positional encodings (computed during the previous tile's backward chain) ----
             wait_buf_free();
-            encode_row(pos, dir, valid, sA, sA + 4 * kABlock, row);
+            pe_store_xyz(pe.x, sA, row);
+            pe_store_dir(pe.d, sA + 4 * kABlock, row);
             publish(true);
             tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
@@ -555,6 +567,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             const uint64_t dsp2 = pk2f(dspre, dspre);
             for (int s = 1; s < ns; ++s) {
                 const BwdStep& B = p.steps[s];
+                if (s == (ns > 3 ? 3 : 1)) prepare_tile(t + 2, pe);   // next tile of this group: its PE is computed inside a long (K = 256) MMA wait
                 CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
                 const long long tr_b0 = CNB_TR_NOW();
                 umma::tc_fence_after();

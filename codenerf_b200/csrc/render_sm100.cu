@@ -232,19 +232,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         const long long tr_t0 = CNB_TR_NOW();
         const int tg = wi * 32 + lane;               // thread index inside the group
         uint32_t bsel = 0;                           // bias staging buffer of the next layer (alternates)
-        for (int r = 0; r < rounds; ++r) {
-            const int t = 2 * r + g;
-            if (t >= T) break;
-            const long long tr_e0 = CNB_TR_NOW();
-            const int64_t lrow = (int64_t)t * kTileRows + row;
-            const bool valid = lrow < nrows;
-            const int64_t grow = row0 + lrow;
-            // ---- inputs: sample position and view direction of this row ----
+        // rays / samples / positional encodings of tile slot t of this group, as packed bf16 rows in registers
+        auto prepare_tile = [&](int t, PeRow& pe) {
+            const int64_t lr = (int64_t)t * kTileRows + row;
+            const bool ok = t < T && lr < nrows;
+            const int64_t gr = row0 + lr;
             float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-            if (valid) {
+            if (ok) {
                 if (p.mode == 0) {
-                    const int64_t lray = grow / N;
-                    const int zi = (int)(grow - lray * N);
+                    const int64_t lray = gr / N;
+                    const int zi = (int)(gr - lray * N);
                     const int64_t ray = p.ray_offset + lray;
                     float o[3];
                     cnb_fetch_ray(p.rs, ray, o, dir);
@@ -254,15 +251,29 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + grow * 3 + k); dir[k] = __ldg(p.viewdir + grow * 3 + k); }
+                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + gr * 3 + k); dir[k] = __ldg(p.viewdir + gr * 3 + k); }
                 }
             }
+            pe_compute_xyz(pos, ok, pe.x);
+            pe_compute_dir(dir, ok, pe.d);
+        };
+        PeRow pe;
+        if (g < T) prepare_tile(g, pe);
+        for (int r = 0; r < rounds; ++r) {
+            const int t = 2 * r + g;
+            if (t >= T) break;
+            const long long tr_e0 = CNB_TR_NOW();
+            const int64_t lrow = (int64_t)t * kTileRows + row;
+            const bool valid = lrow < nrows;
+            const int64_t grow = row0 + lrow;
             int64_t code = 0;
             if (p.n_codes > 1) {
                 code = (p.ray_offset * N + (valid ? grow : row0)) / p.rows_per_code;
                 if (code >= p.n_codes) code = p.n_codes - 1;
             }
-            encode_row(pos, dir, valid, sA, sA + 4 * kABlock, row);
+            // ---- positional encodings (computed during the previous tile's last layers) -> operand blocks ----
+            pe_store_xyz(pe.x, sA, row);
+            pe_store_dir(pe.d, sA + 4 * kABlock, row);
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
             __syncwarp();
@@ -286,6 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 float2 bias2 = make_float2(0.f, 0.f);
                 const bool mine = 2 * tg < L.n_halves * 128;
                 if (staged && mine) bias2 = __ldg(reinterpret_cast<const float2*>(bias) + tg);    // in flight during the wait
+                if (l == nl - 2) prepare_tile(t + 2, pe);      // next tile of this group: its PE is computed inside this wait
                 CNB_TR(tr_wacc, umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u));
                 const long long tr_p0 = CNB_TR_NOW();
                 umma::tc_fence_after();

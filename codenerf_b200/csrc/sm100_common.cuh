@@ -180,57 +180,26 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
     if (MASK && RELU) umma::st_global_hint(mscr + (size_t)CC * kTileRows, ~sgn, acc.mask_policy);   // bit set <=> pre-activation >= +0
 }
 
-// A whole layer: NCC x 32 columns.  tcgen05.ld is latency bound (~300 cycles per 32x32 load, tests/probe_ts.cu),
-// so four loads are in flight at the start and the next two are issued before the previous two are consumed.
+// A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.  (Four in flight, with the registers that
+// setmaxnreg frees, measured no faster and leaves no room for the next tile's prefetched encodings.)
 template <int NCC, int KIND, bool STORE, bool MASK, bool SM = false>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                    const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
-    uint32_t ra[32], rb[32], rc[32], rd[32];
-    umma::tmem_ld32(taddr + 0, ra);
-    umma::tmem_ld32(taddr + 32, rb);
-    umma::tmem_ld32(taddr + 64, rc);
-    umma::tmem_ld32(taddr + 96, rd);
-    umma::tmem_ld_wait();
-    fwd_epilogue32<0, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
-    fwd_epilogue32<1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
-    if constexpr (NCC == 8) {
-        umma::tmem_ld32(taddr + 128, ra);
-        umma::tmem_ld32(taddr + 160, rb);
-    }
-    fwd_epilogue32<2, KIND, STORE, MASK, SM>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
-    fwd_epilogue32<3, KIND, STORE, MASK, SM>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
-    if constexpr (NCC == 8) {
-        umma::tmem_ld32(taddr + 192, rc);
-        umma::tmem_ld32(taddr + 224, rd);
+    auto pair = [&](auto cc_tag) {
+        constexpr int CC = decltype(cc_tag)::value;
+        uint32_t ra[32], rb[32];
+        umma::tmem_ld32(taddr + CC * 32, ra);
+        umma::tmem_ld32(taddr + CC * 32 + 32, rb);
         umma::tmem_ld_wait();
-        fwd_epilogue32<4, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<5, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<6, KIND, STORE, MASK, SM>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<7, KIND, STORE, MASK, SM>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
-    }
-}
-
-// NC (2 or 4) consecutive 32-column chunks of a layer: one thread's share when two warps split the columns of a row.
-// Every pointer / address argument is pre-offset to the thread's first chunk (so the column half is a run-time
-// value and the code exists once); a8 must point at the K-block that holds the first chunk.
-template <int NC, int KIND, bool MASK, bool SM>
-__device__ __forceinline__ void fwd_epilogue_chunks(uint32_t taddr, const float* __restrict__ bias, const uint32_t (&a8)[8],
-                                                    const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
-                                                    HeadAcc& acc, uint32_t* mscr, bool do_store) {
-    // two loads in flight per warp: the second warp of the scheduler (the other column half) hides their latency
-    uint32_t ra[32], rb[32];
-    umma::tmem_ld32(taddr + 0, ra);
-    umma::tmem_ld32(taddr + 32, rb);
-    umma::tmem_ld_wait();
-    fwd_epilogue32<0, KIND, true, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
-    fwd_epilogue32<1, KIND, true, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
-    if constexpr (NC == 4) {
-        umma::tmem_ld32(taddr + 64, ra);
-        umma::tmem_ld32(taddr + 96, rb);
-        umma::tmem_ld_wait();
-        fwd_epilogue32<2, KIND, true, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
-        fwd_epilogue32<3, KIND, true, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, do_store);
+        fwd_epilogue32<CC, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    };
+    pair(std::integral_constant<int, 0>{});
+    pair(std::integral_constant<int, 2>{});
+    if constexpr (NCC == 8) {
+        pair(std::integral_constant<int, 4>{});
+        pair(std::integral_constant<int, 6>{});
     }
 }
 
@@ -412,10 +381,12 @@ __device__ __forceinline__ void issue_gemm_2cta(uint32_t a_base, uint32_t d_base
     __syncwarp();
 }
 
-// PE of one row into the operand blocks -- reference src/model.py:4-7 (x, sines, cosines).
+// PE of one row -- reference src/model.py:4-7 (x, sines, cosines), as packed bf16 pairs in registers.
 // sin/cos(2^i x) by exact doubling from an accurate sincosf(x): error < 2^i * 1e-7, far below bf16.
-// xyz: 63 channels (+1 zero) -> row `row` of a [128 x 64] bf16 block, 128-byte swizzle.
-__device__ __forceinline__ void encode_xyz_row(const float p[3], bool valid, uint8_t* blk0, int row) {
+// Computing (registers) and storing (shared memory) are separate so that a tile's encodings can be prepared while
+// the previous tile still owns the operand buffer.
+struct PeRow { uint32_t x[32]; uint32_t d[16]; };    // xyz: 63 channels (+1 zero); view direction: 27 (+5 zeros)
+__device__ __forceinline__ void pe_compute_xyz(const float p[3], bool valid, uint32_t (&out)[32]) {
     float e[64];
 #pragma unroll
     for (int i = 0; i < 64; ++i) e[i] = 0.f;
@@ -436,14 +407,9 @@ __device__ __forceinline__ void encode_xyz_row(const float p[3], bool valid, uin
         }
     }
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        st_shared_v4(blk0 + row * 128 + ((ch ^ (row & 7)) << 4), umma::pack_bf16(e[ch * 8 + 0], e[ch * 8 + 1]),
-                     umma::pack_bf16(e[ch * 8 + 2], e[ch * 8 + 3]), umma::pack_bf16(e[ch * 8 + 4], e[ch * 8 + 5]),
-                     umma::pack_bf16(e[ch * 8 + 6], e[ch * 8 + 7]));
-    }
+    for (int i = 0; i < 32; ++i) out[i] = umma::pack_bf16(e[2 * i], e[2 * i + 1]);
 }
-// view direction: 27 channels (+5 zeros) -> row `row` of a [128 x 32] bf16 block, 64-byte swizzle.
-__device__ __forceinline__ void encode_dir_row(const float v[3], bool valid, uint8_t* dirblk, int row) {
+__device__ __forceinline__ void pe_compute_dir(const float v[3], bool valid, uint32_t (&out)[16]) {
     float d[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) d[i] = 0.f;
@@ -464,11 +430,29 @@ __device__ __forceinline__ void encode_dir_row(const float v[3], bool valid, uin
         }
     }
 #pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-        st_shared_v4(dirblk + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4), umma::pack_bf16(d[ch * 8 + 0], d[ch * 8 + 1]),
-                     umma::pack_bf16(d[ch * 8 + 2], d[ch * 8 + 3]), umma::pack_bf16(d[ch * 8 + 4], d[ch * 8 + 5]),
-                     umma::pack_bf16(d[ch * 8 + 6], d[ch * 8 + 7]));
-    }
+    for (int i = 0; i < 16; ++i) out[i] = umma::pack_bf16(d[2 * i], d[2 * i + 1]);
+}
+// row `row` of a [128 x 64] bf16 block, 128-byte swizzle
+__device__ __forceinline__ void pe_store_xyz(const uint32_t (&w)[32], uint8_t* blk0, int row) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch)
+        st_shared_v4(blk0 + row * 128 + ((ch ^ (row & 7)) << 4), w[ch * 4 + 0], w[ch * 4 + 1], w[ch * 4 + 2], w[ch * 4 + 3]);
+}
+// row `row` of a [128 x 32] bf16 block, 64-byte swizzle
+__device__ __forceinline__ void pe_store_dir(const uint32_t (&w)[16], uint8_t* dirblk, int row) {
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch)
+        st_shared_v4(dirblk + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4), w[ch * 4 + 0], w[ch * 4 + 1], w[ch * 4 + 2], w[ch * 4 + 3]);
+}
+__device__ __forceinline__ void encode_xyz_row(const float p[3], bool valid, uint8_t* blk0, int row) {
+    uint32_t w[32];
+    pe_compute_xyz(p, valid, w);
+    pe_store_xyz(w, blk0, row);
+}
+__device__ __forceinline__ void encode_dir_row(const float v[3], bool valid, uint8_t* dirblk, int row) {
+    uint32_t w[16];
+    pe_compute_dir(v, valid, w);
+    pe_store_dir(w, dirblk, row);
 }
 __device__ __forceinline__ void encode_row(const float p[3], const float v[3], bool valid, uint8_t* blk0,
                                            uint8_t* dirblk, int row) {
