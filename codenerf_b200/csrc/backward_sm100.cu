@@ -504,6 +504,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
             }
             const long long tr_m0 = CNB_TR_NOW();
+            // ReLU bit words of rgb.0 for step 0: fetched now, used after the compositing (L2 latency overlapped)
+            uint32_t mlast4[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mlast4[c] = umma::ld_global_hint(mscr + ((size_t)(nl - 1) * 8 + c) * kTileRows, pol_keep);
             float sig_pre;
             { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
             const float x = sig_pre + __ldg(p.b_sigma);
@@ -537,10 +541,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             {
                 const float* wrgb_s = smem_fptr(sWrgb, order_token());
                 const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
-                uint32_t mlast = 0u;
 #pragma unroll
                 for (int c8 = 0; c8 < 16; ++c8) {
-                    if ((c8 & 3) == 0) mlast = umma::ld_global_hint(mscr + ((size_t)(nl - 1) * 8 + (c8 >> 2)) * kTileRows, pol_keep);
+                    const uint32_t mlast = mlast4[c8 >> 2];
                     const int col = c8 * 8;
                     uint32_t w[4];
 #pragma unroll
