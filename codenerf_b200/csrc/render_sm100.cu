@@ -104,7 +104,10 @@ __device__ __forceinline__ void composite_ray(const FwdParams& p, const float4* 
 // each CTA streams half of every weight chunk, halving L2 and shared-memory operand traffic per row.
 // MC > 1 (with CG = 1): clusters of MC CTAs with independent M = 128 MMAs whose weight stream is multicast --
 // every stage leaves L2 once per cluster (the weight stream from L2 is what bounds the CG = 1, MC = 1 kernel).
-template <int CG, int MC>
+// EW = 4: each tile has its own four epilogue warps (X / Y groups).  EW = 8: all eight warps drain every accumulator
+// (two per TMEM lane quarter, half of the columns each): half the epilogue latency per tile -- what the CTA-pair
+// kernel needs, whose per-tile chain (epilogue -> remote arrive -> MMA -> multicast commit) is the limit.
+template <int CG, int MC, int EW = 4>
 __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constant__ FwdParams p) {
     static_assert(CG == 1 || MC == 1, "pairs and multicast clusters are alternatives");
     constexpr int kCluster = CG * MC;
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], MC); }
         for (int i = 0; i < kNumStages; ++i) umma::mbar_init(&w_full_peer[i], 1);
-        for (int g = 0; g < 2; ++g) { umma::mbar_init(&a_ready[g], 4 * CG); umma::mbar_init(&acc_full[g], 1); }
+        for (int g = 0; g < 2; ++g) { umma::mbar_init(&a_ready[g], EW * CG); umma::mbar_init(&acc_full[g], 1); }
         final_count[0] = 0; final_count[1] = 0;
         umma::fence_mbar_init();
     }
@@ -215,6 +218,178 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(2, tr_wa); CNB_TR_FLUSH(3, tr_ww); CNB_TR_FLUSH(4, tr_tot);
     }
+    } else if constexpr (EW == 8) {
+        umma::setmaxnreg_inc<kRegsCompute>();
+        // ===== eight epilogue warps serving tiles X and Y alternately, in the order their accumulators complete =====
+        const int q = warp & 3;                      // TMEM lane quarter
+        const int ch = (warp - 4) >> 2;              // column half of a 256-wide layer (64-column half of rgb.0)
+        const int w8 = warp - 4;
+        const int row = q * 32 + lane;
+        const int tid8 = w8 * 32 + lane;             // 0 .. 255
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int N = p.rs.N;
+        uint32_t a8x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) a8x[c] = umma::smem_u32(sA0 + row * 128 + ((c ^ (row & 7)) << 4));
+        float4* sHead = (float4*)(sBias + 2 * kW);   // [128] partial heads of the second column-half warp (second half of the staging area)
+        uint64_t sig0 = 0ull, sig1 = 0ull;           // sigma-head partial sums, per tile slot
+        uint32_t bsel = 0;
+        CNB_TR_DECL(tr_wacc); CNB_TR_DECL(tr_epi); CNB_TR_DECL(tr_enc); CNB_TR_DECL(tr_tot);
+        const long long tr_t0 = CNB_TR_NOW();
+
+        // this thread's part of a tile's encodings: xyz (32 words, ch == 0) or view direction (16 words, ch == 1)
+        auto prepare_tile = [&](int t, uint32_t (&w)[32]) {
+            const int64_t lr = (int64_t)t * kTileRows + row;
+            const bool ok = t < T && lr < nrows;
+            const int64_t gr = row0 + lr;
+            float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+            if (ok) {
+                if (p.mode == 0) {
+                    const int64_t lray = gr / N;
+                    const int zi = (int)(gr - lray * N);
+                    const int64_t ray = p.ray_offset + lray;
+                    float o[3];
+                    cnb_fetch_ray(p.rs, ray, o, dir);
+                    const int64_t seg = ray / p.rs.rays_per_segment;
+                    const float z = __ldg(p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0) + zi);
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + gr * 3 + k); dir[k] = __ldg(p.viewdir + gr * 3 + k); }
+                }
+            }
+            if (ch == 0) pe_compute_xyz(pos, ok, w);
+            else {
+                uint32_t d[16];
+                pe_compute_dir(dir, ok, d);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) w[i] = d[i];
+            }
+        };
+        uint32_t pe0[32], pe1[32];
+        prepare_tile(0, pe0);
+        prepare_tile(1, pe1);
+
+        auto tile_op = [&](const int g, int r, int op) {
+            const int t = 2 * r + g;
+            const int64_t lrow = (int64_t)t * kTileRows + row;
+            const bool valid = lrow < nrows;
+            const int64_t grow = row0 + lrow;
+            uint8_t* sA = sA0 + g * kATile;
+            const uint32_t taddr = tmem + lane_off + (uint32_t)g * 256u;
+            auto publish = [&]() {
+                umma::tc_fence_before();
+                umma::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
+            };
+            if (op == 0) {
+                const long long tr_e0 = CNB_TR_NOW();
+                uint32_t (&pe)[32] = g ? pe1 : pe0;
+                if (ch == 0) pe_store_xyz(pe, sA, row);
+                else {
+                    uint32_t d[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) d[i] = pe[i];
+                    pe_store_dir(d, sA + 4 * kABlock, row);
+                }
+                publish();
+                tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
+                return;
+            }
+            const int l = op - 1;
+            const FwdLayer& L = p.layers[l];
+            const int n_out = L.n_halves * 128;
+            int64_t code = 0;
+            if (p.n_codes > 1) {
+                code = (p.ray_offset * N + (valid ? grow : row0)) / p.rows_per_code;
+                if (code >= p.n_codes) code = p.n_codes - 1;
+            }
+            bool staged = p.stage_bias != 0;
+            int64_t code_b = code;
+            if (staged && p.n_codes > 1) {
+                const int64_t last_l = min((int64_t)t * kTileRows + kTileRows, nrows) - 1;
+                const int64_t c_lo = min((p.ray_offset * N + row0 + (int64_t)t * kTileRows) / p.rows_per_code, (int64_t)p.n_codes - 1);
+                const int64_t c_hi = min((p.ray_offset * N + row0 + last_l) / p.rows_per_code, (int64_t)p.n_codes - 1);
+                staged = c_lo == c_hi;
+                if (staged) code_b = c_lo;
+            }
+            const float* bias_g = L.folded >= 0 ? p.folded + ((size_t)code_b * p.n_folded + L.folded) * kW : L.bias;
+            float bias1 = 0.f;
+            if (staged && tid8 < n_out) bias1 = __ldg(bias_g + tid8);      // in flight during the wait
+            // the next round's encodings are computed inside the waits of the last layers
+            if (l == nl - 3 && g == 0) prepare_tile(t + 2, pe0);
+            if (l == nl - 2 && g == 1) prepare_tile(t + 2, pe1);
+            CNB_TR(tr_wacc, umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u));
+            const long long tr_p0 = CNB_TR_NOW();
+            umma::tc_fence_after();
+            HeadAcc hacc = {l == 0 ? 0ull : (g ? sig1 : sig0), 0ull, 0ull, 0ull, 0ull};
+            uint32_t a8h[8];
+            const int kblk = L.n_halves == 2 ? ch * 2 : ch;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) a8h[c] = a8x[c] + (uint32_t)(g * kATile + kblk * kABlock);
+            const int c0 = L.n_halves == 2 ? ch * 128 : ch * 64;       // first column of this thread
+            const uint32_t th = taddr + (uint32_t)c0;
+            if (staged) {
+                float* sb = sBias + bsel * kW; bsel ^= 1u;
+                if (tid8 < n_out) sb[tid8] = bias1;
+                const uint32_t tok = bar_sync_token(1, 256);
+                const float* bs = smem_fptr(sb, tok) + c0;
+                const float* ws = smem_fptr(sWsig, tok) + c0;
+                const float* wr = smem_fptr(sWrgb, tok) + c0;
+                if (L.kind == 0) fwd_epilogue_chunks<4, 0, true, false, true>(th, bs, a8h, ws, wr, hacc, nullptr);
+                else if (L.kind == 1) fwd_epilogue_chunks<4, 1, true, false, true>(th, bs, a8h, ws, wr, hacc, nullptr);
+                else fwd_epilogue_chunks<2, 2, false, false, true>(th, bs, a8h, ws, wr, hacc, nullptr);
+            } else {
+                const float* bias_t = (L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias) + c0;
+                if (L.kind == 0) fwd_epilogue_chunks<4, 0, true, false, false>(th, bias_t, a8h, p.w_sigma + c0, p.w_rgb2 + c0, hacc, nullptr);
+                else if (L.kind == 1) fwd_epilogue_chunks<4, 1, true, false, false>(th, bias_t, a8h, p.w_sigma + c0, p.w_rgb2 + c0, hacc, nullptr);
+                else fwd_epilogue_chunks<2, 2, false, false, false>(th, bias_t, a8h, p.w_sigma + c0, p.w_rgb2 + c0, hacc, nullptr);
+            }
+            if (g) sig1 = hacc.sig2; else sig0 = hacc.sig2;
+            if (l + 1 < nl) { publish(); tr_epi += (unsigned long long)(CNB_TR_NOW() - tr_p0); return; }
+            tr_epi += (unsigned long long)(CNB_TR_NOW() - tr_p0);
+
+            // ---- heads: the two column halves of a row exchange their partial sums, then one of them finishes ----
+            float sig_p, cr, cg, cb;
+            { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_p = a0 + a1; unpk2(hacc.r2, a0, a1); cr = a0 + a1;
+              unpk2(hacc.g2, a0, a1); cg = a0 + a1; unpk2(hacc.b2, a0, a1); cb = a0 + a1; }
+            if (ch == 1) sHead[row] = make_float4(sig_p, cr, cg, cb);
+            umma::named_bar_sync(1, 256);
+            if (ch == 0) {
+                const float4 o = sHead[row];
+                const float sigma = cnb_softplus(sig_p + o.x + __ldg(p.b_sigma));
+                cr += o.y + __ldg(p.b_rgb2 + 0); cg += o.z + __ldg(p.b_rgb2 + 1); cb += o.w + __ldg(p.b_rgb2 + 2);
+                if (p.mode == 1) {
+                    if (valid) {
+                        p.sigmas[grow] = sigma;
+                        p.rgbs[grow * 3 + 0] = cr; p.rgbs[grow * 3 + 1] = cg; p.rgbs[grow * 3 + 2] = cb;
+                    }
+                } else if (valid) {
+                    sRing[lrow % p.ring_cap] = make_float4(sigma, cr, cg, cb);
+                    if (p.spill_sig) {
+                        p.spill_sig[grow] = sigma;
+                        p.spill_rgb[grow * 3 + 0] = cr; p.spill_rgb[grow * 3 + 1] = cg; p.spill_rgb[grow * 3 + 2] = cb;
+                    }
+                }
+            }
+            umma::named_bar_sync(1, 256);          // samples of the tile are in the ring; sHead may be rewritten
+            if (p.mode == 0) {
+                const int64_t tile_lo = (int64_t)t * kTileRows, tile_hi = min(tile_lo + kTileRows, nrows);
+                const int64_t q_first = tile_lo / N;        // first ray whose last row lies in this tile
+                const int64_t q_last = tile_hi / N - 1;     // last ray completed by the end of this tile
+                for (int64_t qr = q_first + w8; qr <= q_last; qr += 8)
+                    composite_ray(p, sRing, p.ring_cap, qr * N, p.ray_offset + ray0 + qr, lane);
+            }
+        };
+        for (int r = 0; r < rounds; ++r) {
+            const bool two = 2 * r + 1 < T;
+            for (int op = 0; op <= nl; ++op)
+                for (int gi = 0; gi < (two ? 2 : 1); ++gi) tile_op(gi, r, op);      // one call site: the lambda is inlined
+        }
+        tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
+        if (warp == 4) { CNB_TR_FLUSH(5, tr_wacc); CNB_TR_FLUSH(6, tr_epi); CNB_TR_FLUSH(7, tr_enc); CNB_TR_FLUSH(8, tr_tot); }
     } else {
         umma::setmaxnreg_inc<kRegsCompute>();
         // ===== compute groups: PE, per-layer epilogues (TMEM -> bias/ReLU -> bf16 operand), heads, compositing =====
@@ -869,7 +1044,7 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     int64_t units = (total_rows + 2 * kTileRows - 1) / (2 * kTileRows);
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-    static const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();
+    const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();      // read per launch (tests switch it)
     const char* form = getenv("CNB_FWD_KERNEL");       // "ts": the tensor-memory operand experiment (slower)
     if (!use_pairs && form && form[0] == 't') {
         int n_slots = kTsMaxSlots;
@@ -890,7 +1065,11 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     const int mc = (grid == sms && !use_pairs) ? weight_multicast() : 1;
     const bool pairs = use_pairs && grid >= 2;
     if (pairs) { grid &= ~1; CNB_TRY(make_weight_maps(packed, pl.total_bytes, &fp.maps)); }
-    void (*kern)(const FwdParams) = pairs ? k_render_fwd<2, 1> : mc == 4 ? k_render_fwd<1, 4> : mc == 2 ? k_render_fwd<1, 2> : k_render_fwd<1, 1>;
+    const int epi8 = [] { const char* e = getenv("CNB_EPI_WARPS"); return e && atoi(e) == 8 ? 1 : 0; }();
+    const bool ew8 = epi8 && fp.stage_bias;       // the head exchange lives in the staging area
+    void (*kern)(const FwdParams) = pairs ? (ew8 ? k_render_fwd<2, 1, 8> : k_render_fwd<2, 1, 4>)
+                                    : mc == 4 ? k_render_fwd<1, 4> : mc == 2 ? k_render_fwd<1, 2>
+                                    : (ew8 ? k_render_fwd<1, 1, 8> : k_render_fwd<1, 1, 4>);
     const int csize = pairs ? 2 : mc;
     CNB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};

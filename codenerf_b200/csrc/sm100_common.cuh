@@ -203,6 +203,32 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
     }
 }
 
+// NC (2 or 4) consecutive 32-column chunks of a layer: one thread's share when two warps split the columns of a row.
+// Every pointer / address argument is pre-offset to the thread's first chunk (so the column half is a run-time
+// value and the code exists once); a8 must point at the K-block that receives the first chunk.
+template <int NC, int KIND, bool STORE, bool MASK, bool SM>
+__device__ __forceinline__ void fwd_epilogue_chunks(uint32_t taddr, const float* __restrict__ bias, const uint32_t (&a8)[8],
+                                                    const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
+                                                    HeadAcc& acc, uint32_t* mscr) {
+    uint32_t ra[32], rb[32];
+    umma::tmem_ld32(taddr + 0, ra);
+    umma::tmem_ld32(taddr + 32, rb);
+    umma::tmem_ld_wait();
+    if constexpr (NC == 4) {       // the other two loads travel while the first two chunks are consumed
+        uint32_t rc[32], rd[32];
+        umma::tmem_ld32(taddr + 64, rc);
+        umma::tmem_ld32(taddr + 96, rd);
+        fwd_epilogue32<0, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        umma::tmem_ld_wait();
+        fwd_epilogue32<2, KIND, STORE, MASK, SM>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<3, KIND, STORE, MASK, SM>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    } else {
+        fwd_epilogue32<0, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+    }
+}
+
 // ---- warp-uniform pipeline roles ------------------------------------------------------------------
 // Both helpers are executed by a WHOLE warp (so addresses / descriptors live in uniform registers);
 // a single elected lane issues the asynchronous instructions.

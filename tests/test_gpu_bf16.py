@@ -109,8 +109,9 @@ def test_fused_forward_bf16_vs_oracle(N, H, W, n_seg, ray_count, cat, explicit):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"CNB_FWD_KERNEL": "ts"}, {"CNB_CTA_PAIRS": "1"}, {"CNB_WEIGHT_MCAST": "2"}],
-                         ids=["tmem-operands", "cta-pairs", "multicast2"])
+@pytest.mark.parametrize("env", [{"CNB_FWD_KERNEL": "ts"}, {"CNB_CTA_PAIRS": "1"}, {"CNB_WEIGHT_MCAST": "2"},
+                                 {"CNB_EPI_WARPS": "8"}, {"CNB_EPI_WARPS": "8", "CNB_CTA_PAIRS": "1"}],
+                         ids=["tmem-operands", "cta-pairs", "multicast2", "epilogue8", "pairs-epilogue8"])
 def test_forward_kernel_variants_match_default(env):
     """The opt-in forward kernels (measured, not faster) compute the same image as the default:
     full-grid problem (the variants only engage when every SM has work), compared with the default kernel."""
