@@ -1118,6 +1118,8 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     }
     const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256 + 4 * kTileRows * sizeof(float4) +
                         sizeof(float) * (4 * kW + kW + 3 * (kW / 2));
+    // CNB_WEIGHT_MCAST=2: clusters of 2 share one multicast weight stream (+2.5 % in K2 in a back-to-back run, within
+    // the box-to-box noise of the bench: left opt-in)
     const int mc = grid == sms ? weight_multicast() : 1;
     void (*kern)(const BwdParams) = mc == 4 ? k_mlp_bwd<4> : mc == 2 ? k_mlp_bwd<2> : k_mlp_bwd<1>;
     CNB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -526,9 +526,9 @@ inline int make_plan(const cnb_net_config* c, const float* const* P, Plan* pl) {
 }
 
 // CNB_WEIGHT_MCAST = 1 | 2 | 4: CTAs per cluster sharing one multicast weight stream (full-grid launches only).
-inline int weight_multicast() {
+inline int weight_multicast(int dflt = 1) {
     const char* e = getenv("CNB_WEIGHT_MCAST");      // read per launch: tests switch it inside one process
-    const int m = e ? atoi(e) : 1;
+    const int m = e ? atoi(e) : dflt;
     return (m == 2 || m == 4) ? m : 1;
 }
 // Largest grid (a multiple of the cluster size) whose clusters are all co-resident: the kernels are persistent
