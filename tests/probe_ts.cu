@@ -440,6 +440,76 @@ __global__ void __launch_bounds__(384, 1) k_epi(int layers, int nwarps, unsigned
     if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
+// Half-K weight stages: [128 n x 32 k] bf16, 64-byte swizzle, 8 KB; a pair of adjacent stages is one N = 256, K = 32
+// operand (two MMAs), released right after them.  Same 64 KB of ring, twice as many, shorter-lived slots.
+__global__ void __launch_bounds__(128, 1) k_perf_halfk(const uint8_t* wimg, int n_slots, int layers, unsigned long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + 4 * kSlot;
+    __shared__ uint64_t full[32], empty[32], done;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 32; ++i) { umma::mbar_init(&full[i], 1); umma::mbar_init(&empty[i], 1); }
+        umma::mbar_init(&done, 1);
+        umma::fence_mbar_init();
+    }
+    if (warp == 1) umma::tmem_alloc(&tmem_slot, 512);
+    {
+        const int row = threadIdx.x;
+        for (int k = 0; k < 256; ++k)
+            *reinterpret_cast<__nv_bfloat16*>(sA + (k >> 6) * kSlot + umma::sw128_offset(row, k & 63)) = __float2bfloat16(a_val(row, k));
+        umma::fence_proxy_async_smem();
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    umma::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const long long t0 = clock64();
+    const int total = layers * 16;            // 8 KB stages per layer
+    if (warp == 0) {
+        int stage = 0; uint32_t ph = 0;
+        for (int s = 0; s < total; ++s) {
+            umma::mbar_wait(&empty[stage], ph ^ 1);
+            if (umma::elect_one()) {
+                umma::mbar_arrive_expect_tx(&full[stage], 8192);
+                umma::bulk_g2s(sW + stage * 8192, wimg + (size_t)(s & 15) * 8192, 8192, &full[stage]);
+            }
+            __syncwarp();
+            if (++stage == n_slots) { stage = 0; ph ^= 1; }
+        }
+    } else if (warp == 1) {
+        int stage = 0; uint32_t ph = 0;
+        const uint64_t dA = umma::make_sdesc(umma::smem_u32(sA), 16, 1024, umma::SWZ_128B);
+        const uint64_t dB = umma::make_sdesc(umma::smem_u32(sW), 16, 512, umma::SWZ_64B);
+        const uint32_t id256 = umma::make_idesc(128, 256, 0, 0);
+        for (int s = 0; s < total; s += 2) {
+            const int c = (s >> 2) & 3, kh = (s >> 1) & 1;
+            umma::mbar_wait(&full[stage], ph);
+            umma::mbar_wait(&full[stage + 1], ph);
+            umma::tc_fence_after();
+            if (umma::elect_one()) {
+                const uint64_t db = dB + (uint64_t)((stage * 8192) >> 4);
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+                    umma::mma_bf16(tmem, dA + ((c * kSlot) >> 4) + kh * 4 + ks * 2, db + ks * 2, id256, (c | kh | ks) ? 1u : 0u);
+                umma::mma_commit(&empty[stage]); umma::mma_commit(&empty[stage + 1]);
+            }
+            __syncwarp();
+            stage += 2;
+            if (stage >= n_slots) { stage = 0; ph ^= 1; }
+        }
+        if (umma::elect_one()) umma::mma_commit(&done);
+        __syncwarp();
+        umma::mbar_wait(&done, 0);
+        if (threadIdx.x == 32) atomicAdd(cycles, (unsigned long long)(clock64() - t0));
+    }
+    umma::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+}
+
 template <int MODE, int FILL>
 void run_perf(const uint8_t* wimg, int n_slots, int layers, unsigned long long* d_cyc, const char* name) {
     const size_t smem = 1024 + (MODE == 0 ? 4 * kSlot : 0) + (size_t)n_slots * kSlot;
@@ -459,7 +529,7 @@ void run_perf(const uint8_t* wimg, int n_slots, int layers, unsigned long long* 
 
 int main(int argc, char** argv) {
     const bool check_only = argc > 1 && std::string(argv[1]) == "--check-only";
-    uint8_t* wimg; cudaMalloc(&wimg, 8 * kSlot);
+    uint8_t* wimg; cudaMalloc(&wimg, 16 * kSlot);
     k_make_weights<<<8, 256>>>(wimg);
     float *o_ss, *o_ts; cudaMalloc(&o_ss, 128 * 256 * 4); cudaMalloc(&o_ts, 128 * 256 * 4);
     cudaMemset(o_ss, 0, 128 * 256 * 4); cudaMemset(o_ts, 0, 128 * 256 * 4);
@@ -490,6 +560,18 @@ int main(int argc, char** argv) {
     run_perf<1, 0>(wimg, 4, layers, d_cyc, "TS N=128, no refill");
     run_perf<0, 1>(wimg, 4, layers, d_cyc, "SS N=256, streamed");
     run_perf<0, 1>(wimg, 8, layers, d_cyc, "SS N=256, streamed");
+    for (int ns : {8, 12}) {
+        const size_t hsm = 1024 + 4 * kSlot + (size_t)ns * 8192;
+        cudaFuncSetAttribute(k_perf_halfk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm);
+        for (int rep = 0; rep < 2; ++rep) {
+            cudaMemset(d_cyc, 0, 8);
+            k_perf_halfk<<<148, 128, hsm>>>(wimg, ns, layers, d_cyc);
+            cudaError_t e2 = cudaDeviceSynchronize();
+            unsigned long long c = 0; cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost);
+            if (rep) printf("TS_PROBE perf %-28s slots=%2d: %8.1f cycles/layer (8 KB half-K stages, %d KB ring)  err=%s\n", "SS N=256, streamed", ns,
+                            (double)c / 148.0 / layers, ns * 8, cudaGetErrorName(e2));
+        }
+    }
     run_perf<1, 1>(wimg, 4, layers, d_cyc, "TS N=128, streamed");
     run_perf<1, 1>(wimg, 8, layers, d_cyc, "TS N=128, streamed");
     run_perf<1, 1>(wimg, 12, layers, d_cyc, "TS N=128, streamed");
