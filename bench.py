@@ -128,7 +128,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "srncar training step, objects x 2048 rays x 64 samples, fwd+bwd", "sample": sample},
+            "config": {"workload": f"srncar.json training step: {args.objects} objects x {RAYS_PER_OBJECT} rays x {N_SAMPLES} samples "
+                                   "per GPU, fused forward + L2 loss + backward (weights, biases, codes)",
+                       "net": "W=256, 3 shape + 1 texture blocks, latent 256", "view": "128x128", "sample": sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
