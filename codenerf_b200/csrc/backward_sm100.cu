@@ -10,7 +10,7 @@
 //      the stashed tiles read back as MN-major UMMA operands (same bytes, no transpose).
 //
 // Why the weight gradient is a second kernel: one layer's dW (256 x 256 fp32) fills all of TMEM,
-// so it cannot be accumulated on chip next to the per-tile chain; see DESIGN.md section 5.
+// so it cannot be accumulated on chip next to the per-tile chain; see DESIGN.md section 4.
 //
 // Reference semantics: autograd of src/model.py:36-53 (what loss.backward() does in
 // src/trainer.py:82 and src/optimizer.py:92).
