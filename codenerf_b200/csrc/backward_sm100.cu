@@ -42,6 +42,7 @@ struct BwdStep {
 };
 
 struct BwdParams {
+    WeightMaps maps;                // tensor maps of the packed weights (CTA-pair kernel)
     int n_layers, n_steps;
     FwdLayer layers[kMaxLayers];
     BwdStep steps[kMaxLayers];
@@ -238,8 +239,14 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
 
 // MC > 1: clusters of MC CTAs share one multicast weight stream (see produce_stages); every CTA of a cluster runs
 // the same number of tile slots, the surplus ones as phantom tiles (all rows invalid, nothing written).
-template <int MC>
+// CG = 2: CTA pairs (tcgen05 cta_group::2, M = 256 = one tile of each CTA): every CTA streams half of each weight
+// chunk and reads half of the B operand -- 128 KB less shared-memory traffic per tile and GEMM, which is what bounds
+// this kernel; the leader CTA issues the MMAs, the epilogue warps of both CTAs arrive on its
+// a_ready barriers, accumulator / ring-slot commits are multicast to both.
+template <int MC, int CG = 1>
 __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constant__ BwdParams p) {
+    static_assert(CG == 1 || MC == 1, "pairs and multicast clusters are alternatives");
+    constexpr int kCluster = CG * MC;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sA0 = smem;
@@ -266,25 +273,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     const int64_t tbase = tiles / gridDim.x, trem = tiles % gridDim.x;
     const int64_t tile0 = (int64_t)blockIdx.x * tbase + min((int64_t)blockIdx.x, trem);
     const int T_own = (int)(tbase + ((int64_t)blockIdx.x < trem ? 1 : 0));
-    const uint32_t rank = MC > 1 ? umma::cluster_ctarank() : 0u;
-    const int T = MC > 1 ? (int)(tbase + ((int64_t)(blockIdx.x - rank) < trem ? 1 : 0)) : T_own;   // cluster-uniform
+    const uint32_t rank = kCluster > 1 ? umma::cluster_ctarank() : 0u;
+    const int T = kCluster > 1 ? (int)(tbase + ((int64_t)(blockIdx.x - rank) < trem ? 1 : 0)) : T_own;   // cluster-uniform
     const int rounds = (T + 1) >> 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], MC); }
         for (int g = 0; g < 2; ++g) {
-            umma::mbar_init(&a_ready[g], 4); umma::mbar_init(&acc_full[g], 1);
+            umma::mbar_init(&a_ready[g], 4 * CG); umma::mbar_init(&acc_full[g], 1);
             umma::mbar_init(&aux_ready[g], 4); umma::mbar_init(&buf_free[g], 1);
         }
         umma::fence_mbar_init();
     }
-    if (warp == 1) umma::tmem_alloc(tmem_slot, 512);
+    if (warp == 1) { if (CG == 2) umma::tmem_alloc2(tmem_slot, 512); else umma::tmem_alloc(tmem_slot, 512); }
     for (int i = threadIdx.x; i < kW; i += kBwdThreads) sWsig[i] = __ldg(p.w_sigma + i);
     for (int i = threadIdx.x; i < 3 * (kW / 2); i += kBwdThreads) sWrgb[i] = __ldg(p.w_rgb2 + i);
     umma::tc_fence_before();
-    if (MC > 1) umma::cluster_sync_all(); else __syncthreads();
+    if (kCluster > 1) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // a_ready lives in the leader CTA of a pair: the partner's epilogue warps arrive on it remotely
+    const uint32_t a_ready_addr0 = CG == 2 ? umma::mapa(umma::smem_u32(&a_ready[0]), 0) : 0u;
 
     if (warp < 4) {
     umma::setmaxnreg_dec<kRegsAux>();
@@ -299,10 +308,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     if (op < nl) {
                         const FwdLayer& L = p.layers[op];
                         const int n_dir = L.has_dir ? L.n_halves : 0;
-                        produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
+                        if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
+                        else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                     } else {
                         const BwdStep& B = p.steps[op - nl + 1];
-                        produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
+                        if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph);
+                        else produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                     }
                 }
     } else if (warp == 1) {
@@ -317,10 +328,16 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     int n_kchunks, n_halves, has_dir;
                     if (op < nl) { n_kchunks = p.layers[op].n_kchunks; n_halves = p.layers[op].n_halves; has_dir = p.layers[op].has_dir; }
                     else { n_kchunks = p.steps[op - nl + 1].n_kchunks; n_halves = 2; has_dir = 0; }
-                    CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
+                    if (CG == 2 && rank != 0) continue;          // the partner CTA issues no MMAs
+                    if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
+                    else CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
                     umma::tc_fence_after();
-                    issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
-                                   n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
+                    if (CG == 2)
+                        issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                                        n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
+                    else
+                        issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                                       n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
                 }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(0, tr_wa); CNB_TR_FLUSH(1, tr_ww); CNB_TR_FLUSH(2, tr_tot);
@@ -417,7 +434,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) { if (to_mma) umma::mbar_arrive(&a_ready[g]); umma::mbar_arrive(&aux_ready[g]); }
+            if (lane == 0) {
+                if (to_mma) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
+                umma::mbar_arrive(&aux_ready[g]);
+            }
             ++wp;
         };
 
@@ -591,8 +611,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         }
     }
     umma::tc_fence_before();
-    if (MC > 1) umma::cluster_sync_all(); else __syncthreads();
-    if (warp == 1) umma::tmem_dealloc(tmem, 512);
+    if (kCluster > 1) umma::cluster_sync_all(); else __syncthreads();
+    if (warp == 1) { if (CG == 2) umma::tmem_dealloc2(tmem, 512); else umma::tmem_dealloc(tmem, 512); }
 }
 
 // ===========================================================================
@@ -1120,8 +1140,11 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
                         sizeof(float) * (4 * kW + kW + 3 * (kW / 2));
     // CNB_WEIGHT_MCAST=2: clusters of 2 share one multicast weight stream (+2.5 % in K2 in a back-to-back run, within
     // the box-to-box noise of the bench: left opt-in)
-    const int mc = grid == sms ? weight_multicast() : 1;
-    void (*kern)(const BwdParams) = mc == 4 ? k_mlp_bwd<4> : mc == 2 ? k_mlp_bwd<2> : k_mlp_bwd<1>;
+    const int use_pairs = [] { const char* e = getenv("CNB_BWD_PAIRS"); return e ? atoi(e) : 0; }();     // read per launch
+    const bool pairs = use_pairs && grid == sms;
+    const int mc = pairs ? 2 : (grid == sms ? weight_multicast() : 1);      // cluster size
+    if (pairs) CNB_TRY(make_weight_maps(packed, pl.total_bytes, &bp.maps));
+    void (*kern)(const BwdParams) = pairs ? k_mlp_bwd<1, 2> : mc == 4 ? k_mlp_bwd<4> : mc == 2 ? k_mlp_bwd<2> : k_mlp_bwd<1>;
     CNB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;

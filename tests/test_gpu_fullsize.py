@@ -106,3 +106,35 @@ def test_backward_is_linear_in_the_seed():
     for a, b in zip(g1, g2):
         s = float(b.abs().max())
         assert s > 0 and float((a * 4.0 - b).abs().max()) <= 1e-4 * s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("env", [{"CNB_BWD_PAIRS": "1"}, {"CNB_WEIGHT_MCAST": "2"}, {"CNB_K3_OVERLAP": "1"}],
+                         ids=["cta-pairs", "multicast2", "k3-overlap"])
+def test_backward_kernel_variants_match_default(env):
+    """The opt-in forms of the training step (measured, not faster) give the default's gradients."""
+    from codenerf_b200 import _lib, ops
+    model, t, bundle = _batch()
+    params = model.param_list(); packed = model._packed.get(model._cfg, params)
+    n_par = sum(p.numel() for p in params)
+
+    def step():
+        dP = torch.zeros(n_par, device="cuda")
+        rb = bundle(0, N_OBJ).args(t["sc"], t["tc"])
+        out = ops.render_train_step(model._cfg, params, packed, rb, _lib.PRECISION_BF16, t["tgt"], 1.0, dP, want_outputs=True)
+        torch.cuda.synchronize()
+        return [dP] + [o for o in out if o is not None]
+
+    base = step()
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        got = step()
+    finally:
+        for k, v in old.items():
+            if v is None: os.environ.pop(k, None)
+            else: os.environ[k] = v
+    _no_timeouts()
+    for a, b in zip(got, base):
+        s = float(b.abs().max())
+        assert float((a - b).abs().max()) <= 1e-4 * max(s, 1e-30)
