@@ -20,6 +20,12 @@
 using namespace sm100;
 
 #ifdef CNB_TRACE
+extern "C" int cnb_debug_events_bwd(unsigned long long* out, unsigned int* counts, int reset) {
+    if (out && cudaMemcpyFromSymbol(out, sm100::g_events, sizeof(unsigned long long) * 4 * 16384) != cudaSuccess) return -1;
+    if (counts && cudaMemcpyFromSymbol(counts, sm100::g_event_count, sizeof(unsigned int) * 4) != cudaSuccess) return -1;
+    if (reset) { unsigned int z[4] = {}; if (cudaMemcpyToSymbol(sm100::g_event_count, z, sizeof(z)) != cudaSuccess) return -1; }
+    return 0;
+}
 extern "C" int cnb_debug_trace_bwd(unsigned long long* out32, int reset) {
     if (out32 && cudaMemcpyFromSymbol(out32, sm100::g_trace, sizeof(unsigned long long) * 32) != cudaSuccess) return -1;
     if (reset) { unsigned long long z[32] = {}; if (cudaMemcpyToSymbol(sm100::g_trace, z, sizeof(z)) != cudaSuccess) return -1; }
@@ -331,6 +337,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     if (CG == 2 && rank != 0) continue;          // the partner CTA issues no MMAs
                     if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
                     else CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
+                    CNB_EV(lane, 0, (1 << 12) | (g << 8) | op);          // operands ready, issue starts
                     umma::tc_fence_after();
                     if (CG == 2)
                         issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
@@ -338,6 +345,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     else
                         issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
                                        n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
+                    CNB_EV(lane, 0, (2 << 12) | (g << 8) | op);          // all MMAs of the op issued
                 }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(0, tr_wa); CNB_TR_FLUSH(1, tr_ww); CNB_TR_FLUSH(2, tr_tot);
@@ -489,6 +497,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             pe_store_xyz(pe.x, sA, row);
             pe_store_dir(pe.d, sA + 4 * kABlock, row);
             publish(true);
+            if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (6 << 12) | (g << 8));               // encodings stored: tile starts
             tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
             // ---- forward chain (recompute) ----
@@ -499,6 +508,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 float2 bias2 = make_float2(0.f, 0.f);
                 if (2 * tg < L.n_halves * 128) bias2 = __ldg(reinterpret_cast<const float2*>(bias_g) + tg);   // in flight during the wait
                 CNB_TR(tr_wacc_f, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | l);      // accumulator visible: epilogue starts
                 const long long tr_p0 = CNB_TR_NOW();
                 umma::tc_fence_after();
                 const bool last = (l + 1 == nl);
@@ -521,6 +531,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 else if (store) fwd_epilogue_layer<4, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                 else fwd_epilogue_layer<4, 0, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                 if (store) publish(!last);
+                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | l);      // epilogue done, operand published
                 tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
             }
             const long long tr_m0 = CNB_TR_NOW();
@@ -584,6 +595,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 }
             }
             publish(ns > 1);
+            if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (5 << 12) | (g << 8) | nl);         // compositing + step 0 done
             tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
 
             // ---- input-gradient chain ----
@@ -592,6 +604,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 const BwdStep& B = p.steps[s];
                 if (s == (ns > 3 ? 3 : 1)) prepare_tile(t + 2, pe);   // next tile of this group: its PE is computed inside a long (K = 256) MMA wait
                 CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | (nl + s - 1));
                 const long long tr_b0 = CNB_TR_NOW();
                 umma::tc_fence_after();
                 wait_buf_free();
@@ -601,6 +614,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                 else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                 publish(s + 1 < ns);
+                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | (nl + s - 1));
                 tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
             }
         }

@@ -32,7 +32,13 @@ static __device__ unsigned long long g_trace[32];   // one copy per translation 
 #define CNB_TR(acc, ...) do { const long long t_ = clock64(); __VA_ARGS__; (acc) += (unsigned long long)(clock64() - t_); } while (0)
 #define CNB_TR_PTR(ptr, ...) do { const long long t_ = clock64(); __VA_ARGS__; if (ptr) *(ptr) += (unsigned long long)(clock64() - t_); } while (0)
 #define CNB_TR_FLUSH(slot, acc) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_trace[slot], (acc)); } while (0)
+// event log of CTA 0 (timeline of the pipeline): lane 0 of a warp appends (clock, code)
+static __device__ unsigned long long g_events[4][16384];
+static __device__ unsigned int g_event_count[4];
+#define CNB_EV(lane_, slot_, code_) do { if (blockIdx.x == 0 && (lane_) == 0) { const unsigned int i_ = g_event_count[slot_]++; \
+    if (i_ < 16384u) g_events[slot_][i_] = ((unsigned long long)(clock64() & 0xffffffffffffull) << 16) | (unsigned long long)((code_) & 0xffff); } } while (0)
 #else
+#define CNB_EV(lane_, slot_, code_) do { } while (0)
 #define CNB_TR_NOW() 0ll
 #define CNB_TR_DECL(name) unsigned long long name = 0ull; (void)name
 #define CNB_TR(acc, ...) do { __VA_ARGS__; } while (0)
