@@ -26,6 +26,16 @@ class CodeFitter:
         for p in self.model.parameters():          # reference never steps them (optimizer.py:195-198)
             p.requires_grad_(False)
 
+    @classmethod
+    def from_checkpoint(cls, path, hpams, device="cuda", precision="bf16", **kw):
+        """optimizer.py:205-216: build the module, load `models.pth` on the CPU, move it to the device; returns
+        (fitter, mean shape code, mean texture code) -- the initial codes of every test object."""
+        from .checkpoint import load_models
+        from .model import CodeNeRF
+        model = CodeNeRF(**hpams["net_hyperparams"], precision=precision)
+        _, mean_shape, mean_texture = load_models(path, model)
+        return cls(model.to(device), hpams, **kw), mean_shape, mean_texture
+
     def _bundle(self, focal, H, W, pose, z, dev):
         n_rays = H * W
         n_chunks = n_rays // self.B

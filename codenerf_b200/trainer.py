@@ -92,5 +92,10 @@ class Trainer:
 
     def state(self):
         """The dict reference save_models writes to models.pth (trainer.py:165-174)."""
-        return {"model_params": self.model.state_dict(), "shape_code_params": self.shape_codes.state_dict(),
-                "texture_code_params": self.texture_codes.state_dict(), "niter": self.niter, "nepoch": self.nepoch}
+        from .checkpoint import models_dict
+        return models_dict(self.model, self.shape_codes, self.texture_codes, self.niter, self.nepoch)
+
+    def save_models(self, save_dir, iteration=None):
+        """trainer.py:165-174: `models.pth` (+ `<iteration>.pth`) in the reference's wire format."""
+        from .checkpoint import save_models
+        return save_models(save_dir, self.model, self.shape_codes, self.texture_codes, self.niter, self.nepoch, iteration)
