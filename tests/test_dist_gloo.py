@@ -58,7 +58,7 @@ def test_two_rank_gradient_allreduce_equals_single_process():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
-    mgr = mp.Manager()
+    mgr = mp.get_context("spawn").Manager()      # no fork() from a multi-threaded pytest process
     out = mgr.dict()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     flat, _ = syn.make_params(0)
