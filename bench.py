@@ -200,6 +200,8 @@ def run_ours(args):
     def step(c2w_t, z_t, tgt_t):
         rb = make_bundle(c2w_t, z_t).args(d_sc, d_tc)
         dP.zero_()
+        if prec == _lib.PRECISION_BF16:      # a training step follows an optimiser step: the bf16 operand copies are rebuilt
+            model._packed.get(model._cfg, params, refresh=True)
         out = ops.render_train_step(model._cfg, params, packed, rb, prec, tgt_t, 1.0, dP, want_outputs=False)
         if world > 1:
             dist.all_reduce(dP)             # the one collective of the path: 2.86 MB MLP gradient

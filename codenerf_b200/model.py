@@ -26,7 +26,8 @@ class _MLPFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, xyz, viewdir, shape_codes, tex_codes, samples_per_code, *params):
         cfg, prec = module._cfg, _lib.precision_id(module.precision)
-        packed = module._packed.get(cfg, params) if prec == _lib.PRECISION_BF16 else None
+        training = any(p.requires_grad for p in params)         # see ops.PackedWeights: versions are not reliable then
+        packed = module._packed.get(cfg, params, refresh=training) if prec == _lib.PRECISION_BF16 else None
         sig, col = ops.mlp_forward(cfg, params, packed, xyz, viewdir, shape_codes, tex_codes, samples_per_code, prec)
         ctx.module, ctx.spc = module, samples_per_code
         ctx.save_for_backward(xyz, viewdir, shape_codes, tex_codes, *params)

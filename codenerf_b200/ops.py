@@ -55,15 +55,23 @@ def param_pointer_table(params):
 
 
 class PackedWeights:
-    """bf16 tensor-core operand copies of the layer matrices; rebuilt when any parameter changes."""
+    """bf16 tensor-core operand copies of the layer matrices (derived state).
+
+    Rebuilt when a parameter's storage or version counter changes -- and, with `refresh=True`, unconditionally:
+    fused optimisers (`torch.optim.AdamW(..., fused=True)`) and writes through `.data` update parameters WITHOUT
+    bumping the version counter, so every caller whose parameters may be training passes `refresh=True` on the
+    forward call (one ~15 us kernel).  Frozen models keep the cached copy; `invalidate()` drops it by hand."""
 
     def __init__(self):
         self.buf = None
         self.key = None
 
-    def get(self, cfg, params):
+    def invalidate(self):
+        self.key = None
+
+    def get(self, cfg, params, refresh=False):
         key = tuple((p.data_ptr(), p._version) for p in params)
-        if self.buf is None or self.key != key:
+        if self.buf is None or self.key != key or refresh:
             L = _lib.load()
             n = L.cnb_packed_weights_bytes(ctypes.byref(cfg))
             if self.buf is None or self.buf.numel() < n or self.buf.device != params[0].device:

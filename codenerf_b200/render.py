@@ -40,7 +40,8 @@ class _RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, module, bundle, shape_codes, tex_codes, *params):
         cfg, prec = module._cfg, _lib.precision_id(module.precision)
-        packed = module._packed.get(cfg, params) if prec == _lib.PRECISION_BF16 else None
+        training = any(p.requires_grad for p in params)         # see ops.PackedWeights: versions are not reliable then
+        packed = module._packed.get(cfg, params, refresh=training) if prec == _lib.PRECISION_BF16 else None
         rb = bundle.args(shape_codes, tex_codes)
         rgb, depth, acc = ops.render_forward(cfg, params, packed, rb, prec)
         ctx.module, ctx.bundle = module, bundle

@@ -44,10 +44,11 @@ class Trainer:
 
     def set_optimizers(self):                                                                    # trainer.py:114-120
         lr1, lr2 = self.get_learning_rate()
+        # one fused multi-tensor kernel on the GPU (same update rule; an iteration on one view is launch bound)
         self.opts = torch.optim.AdamW([
             {"params": self.model.parameters(), "lr": lr1},
             {"params": self.shape_codes.parameters(), "lr": lr2},
-            {"params": self.texture_codes.parameters(), "lr": lr2}])
+            {"params": self.texture_codes.parameters(), "lr": lr2}], fused=self.device.type == "cuda")
 
     def train_view(self, focal, H, W, imgs, poses, obj_idx):
         """One iteration of trainer.py:57-96 for one object: imgs [n_views, H*W, 3], poses [n_views, 4, 4].
@@ -65,7 +66,8 @@ class Trainer:
         for k in range(imgs.shape[0]):
             self.opts.zero_grad()                                        # trainer.py:64 (discards earlier views)
             z = make_z_vals(self.hpams["near"], self.hpams["far"], self.hpams["N_samples"]).to(dev)   # one draw per view
-            packed = self.model._packed.get(cfg, params) if prec == _lib.PRECISION_BF16 else None
+            # repacked once per iteration: the (fused) optimiser step does not bump the parameters' version counters
+            packed = self.model._packed.get(cfg, params, refresh=(k == 0)) if prec == _lib.PRECISION_BF16 else None
             sc = self.shape_codes.weight[obj_idx:obj_idx + 1]
             tc = self.texture_codes.weight[obj_idx:obj_idx + 1]
             pix = torch.arange(n_chunks, dtype=torch.int32, device=dev) * B
@@ -77,7 +79,7 @@ class Trainer:
             tgt = imgs[k].to(dev).float().reshape(n_rays, 3).contiguous()
             _, _, _, sq, dsc, dtc = ops.render_train_step(cfg, params, packed, rb, prec, tgt, 1.0, dP, want_outputs=False)
             for p, g in zip(params, ops.split_flat_grads(cfg, dP, params)):
-                p.grad = g.clone() if p.grad is None else p.grad + g
+                p.grad = g if p.grad is None else p.grad + g          # views of this view's flat gradient vector
             # regulariser on the first chunk (trainer.py:76-79): coef * mean(|shape| + |tex|)
             coef = self.hpams["loss_reg_coef"]
             gs = torch.zeros_like(self.shape_codes.weight)

@@ -269,3 +269,39 @@ def test_latent_only_backward_bf16():
     assert U.rel_err(sc.grad.cpu().numpy(), np.concatenate(ds_ref)) < 4e-2
     assert U.rel_err(tc.grad.cpu().numpy(), np.concatenate(dt_ref)) < 4e-2
     assert all(p.grad is None for p in model.parameters())
+
+
+@pytest.mark.gpu
+def test_packed_weights_follow_updates_that_do_not_bump_versions():
+    """Fused optimisers and `.data` writes change parameters without touching their version counters; the bf16 operand
+    copies must still follow (ops.PackedWeights: refreshed on every forward of a model that may be training)."""
+    import codenerf_b200 as cn
+    model, flat, bundle, scodes, tcodes, zs, ref = _fused_case(64, 32, 32, 2, 128, syn.SRN_CARS, False, with_ref=False)
+    sc, tc = torch.from_numpy(scodes).cuda(), torch.from_numpy(tcodes).cuda()
+
+    def fresh_render(src):
+        m, _ = U.make_model("bf16")
+        m.load_state_dict(src.state_dict())
+        for q in m.parameters():
+            q.requires_grad_(False)
+        with torch.no_grad():
+            return m, cn.render(m, bundle, sc, tc)[0]
+
+    rgb0 = cn.render(model, bundle, sc, tc)[0].detach().clone()
+    p = dict(model.named_parameters())["encoding_shape.weight"]       # a pure GEMM operand: only the packed copy is read
+    v = p._version
+    opt = torch.optim.AdamW([p], lr=0.05, fused=True)
+    p.grad = torch.ones_like(p)
+    opt.step()
+    assert p._version == v                      # the hazard this test is about
+    rgb1 = cn.render(model, bundle, sc, tc)[0].detach()
+    frozen, want = fresh_render(model)
+    assert not torch.equal(rgb1, rgb0) and torch.equal(rgb1, want)
+    # frozen models cache the packed copy; invalidate() is the manual switch for writes through .data
+    dict(frozen.named_parameters())["encoding_shape.weight"].data.mul_(3.0)
+    with torch.no_grad():
+        stale = cn.render(frozen, bundle, sc, tc)[0]
+        frozen._packed.invalidate()
+        fresh = cn.render(frozen, bundle, sc, tc)[0]
+    _, want2 = fresh_render(frozen)
+    assert torch.equal(stale, want) and not torch.equal(fresh, stale) and torch.equal(fresh, want2)
