@@ -510,6 +510,44 @@ __global__ void __launch_bounds__(128, 1) k_perf_halfk(const uint8_t* wimg, int 
     if (warp == 1) umma::tmem_dealloc(tmem, 512);
 }
 
+// SM-to-SM bulk copy bandwidth: every CTA of a cluster sends `bytes` from its shared memory to the next CTA's shared
+// memory (a ring), `iters` times, with cp.async.bulk.shared::cluster.shared::cta completing on the receiver's mbarrier.
+__global__ void __launch_bounds__(64, 1) k_dsmem(int csize, uint32_t bytes, int iters, unsigned long long* cycles) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* src = smem;                 // what this CTA sends
+    uint8_t* dst = smem + 65536;         // where the previous CTA of the ring writes
+    __shared__ uint64_t rx_bar;          // completes when the upstream neighbour's data has landed here
+    __shared__ uint64_t tx_credit;       // the downstream neighbour has consumed my previous message and re-armed
+    const uint32_t rank = umma::cluster_ctarank();
+    if (threadIdx.x == 0) {
+        umma::mbar_init(&rx_bar, 1); umma::mbar_init(&tx_credit, 1); umma::fence_mbar_init();
+        umma::mbar_arrive_expect_tx(&rx_bar, bytes);              // armed for round 0 before anybody may send
+    }
+    for (uint32_t i = threadIdx.x; i < bytes / 4; i += blockDim.x) ((uint32_t*)src)[i] = i * 2654435761u + rank;
+    umma::fence_proxy_async_smem();
+    umma::cluster_sync_all();
+    const uint32_t next = (rank + 1) % (uint32_t)csize, prev = (rank + (uint32_t)csize - 1) % (uint32_t)csize;
+    const uint32_t dst_remote = umma::mapa(umma::smem_u32(dst), next);
+    const uint32_t bar_remote = umma::mapa(umma::smem_u32(&rx_bar), next);
+    const uint32_t credit_remote = umma::mapa(umma::smem_u32(&tx_credit), prev);
+    const long long t0 = clock64();
+    if (threadIdx.x == 0) {
+        for (int it = 0; it < iters; ++it) {
+            if (it > 0) umma::mbar_wait_cluster(&tx_credit, (uint32_t)(it - 1) & 1u);
+            asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst_remote), "r"(umma::smem_u32(src)), "r"(bytes), "r"(bar_remote) : "memory");
+            umma::mbar_wait_cluster(&rx_bar, (uint32_t)it & 1u);  // my inbox is full
+            if (it + 1 < iters) umma::mbar_arrive_expect_tx(&rx_bar, bytes);
+            umma::mbar_arrive_cluster(credit_remote);             // upstream may send the next round
+        }
+    }
+    __syncthreads();
+    const long long dt = clock64() - t0;
+    umma::cluster_sync_all();
+    if (threadIdx.x == 0) atomicMax(cycles, (unsigned long long)dt);
+}
+
 template <int MODE, int FILL>
 void run_perf(const uint8_t* wimg, int n_slots, int layers, unsigned long long* d_cyc, const char* name) {
     const size_t smem = 1024 + (MODE == 0 ? 4 * kSlot : 0) + (size_t)n_slots * kSlot;
@@ -529,7 +567,22 @@ void run_perf(const uint8_t* wimg, int n_slots, int layers, unsigned long long* 
 
 int main(int argc, char** argv) {
     const bool check_only = argc > 1 && std::string(argv[1]) == "--check-only";
+    const bool dsmem_only = argc > 1 && std::string(argv[1]) == "--dsmem-only";
     uint8_t* wimg; cudaMalloc(&wimg, 16 * kSlot);
+    if (dsmem_only) {
+        unsigned long long* dc; cudaMalloc(&dc, 8); cudaMemset(dc, 0, 8);
+        const size_t dsm = 1024 + 2 * 65536;
+        cudaFuncSetAttribute(k_dsmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = dsm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e1 = cudaLaunchKernelEx(&cfg, k_dsmem, 2, 4096u, 2, dc);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        printf("dsmem-only launch=%s sync=%s\n", cudaGetErrorName(e1), cudaGetErrorName(e2));
+        return 0;
+    }
     k_make_weights<<<8, 256>>>(wimg);
     float *o_ss, *o_ts; cudaMalloc(&o_ss, 128 * 256 * 4); cudaMalloc(&o_ts, 128 * 256 * 4);
     cudaMemset(o_ss, 0, 128 * 256 * 4); cudaMemset(o_ts, 0, 128 * 256 * 4);
@@ -604,6 +657,26 @@ int main(int argc, char** argv) {
                     if (rep) printf("TS_PROBE epilogue warps=%d mma=%d: %7.1f cycles per 128x256 layer per tile  err=%s\n", nw, with_mma, (double)c / 2000.0, cudaGetErrorName(e2));
                 }
             }
+    }
+    for (int cs : {2, 4, 8}) {
+        const uint32_t bytes = 65536; const int iters = 200;
+        const size_t dsm = 1024 + 2 * 65536;
+        cudaFuncSetAttribute(k_dsmem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsm);
+        cudaFuncSetAttribute(k_dsmem, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((148 / cs) * cs); cfg.blockDim = dim3(64); cfg.dynamicSmemBytes = dsm;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0; cudaOccupancyMaxActiveClusters(&ncl, k_dsmem, &cfg);
+        if (ncl > 0 && ncl * cs < (int)cfg.gridDim.x) cfg.gridDim = dim3(ncl * cs);
+        cudaMemset(d_cyc, 0, 8);
+        cudaError_t e1 = cudaLaunchKernelEx(&cfg, k_dsmem, cs, bytes, iters, d_cyc);
+        cudaError_t e2 = cudaDeviceSynchronize();
+        unsigned long long c = 0; cudaMemcpy(&c, d_cyc, 8, cudaMemcpyDeviceToHost);
+        unsigned int to = 0; cudaMemcpyFromSymbol(&to, umma::g_umma_timeout, sizeof(to));
+        printf("TS_PROBE dsmem ring of %d CTAs (%u clusters): %7.1f cycles per 64 KB hop = %5.1f B/clk per SM  launch=%s sync=%s timeout=%u\n",
+               cs, cfg.gridDim.x / cs, (double)c / iters, 65536.0 * iters / (double)c, cudaGetErrorName(e1), cudaGetErrorName(e2), to);
     }
     run_shared<1>(wimg, 10, layers / 2, d_cyc, "TS N=128, X+Y share a pass");
     run_shared<1>(wimg, 12, layers / 2, d_cyc, "TS N=128, X+Y share a pass");
