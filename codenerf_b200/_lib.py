@@ -8,6 +8,9 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcodenerf_b200.so")
+# CNB_LIB=trace selects the instrumented build (`python -m codenerf_b200.build --trace`); perf-debugging scripts only
+if os.environ.get("CNB_LIB") == "trace":
+    LIB_PATH = os.path.join(_HERE, "libcodenerf_b200_trace.so")
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1

@@ -1,4 +1,10 @@
-"""Build libcodenerf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libcodenerf_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+`python -m codenerf_b200.build [--force] [-v] [--trace]`.  `--trace` builds the instrumented variant
+(`-DCNB_TRACE`, clock64 accounting of the pipeline roles) as libcodenerf_b200_trace.so next to the product
+library; scripts select it with `CNB_LIB=trace` (see _lib.py).  The product library never contains the
+instrumentation.
+"""
 import os
 import subprocess
 import sys
@@ -6,9 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcodenerf_b200.so")
+LIB_TRACE = os.path.join(HERE, "libcodenerf_b200_trace.so")
 SOURCES = ["api.cu", "rays.cu", "mlp_fp32.cu", "render_sm100.cu", "backward_sm100.cu"]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "--use_fast_math=false" if False else "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -18,25 +24,26 @@ def _nvcc():
     return "nvcc"
 
 
-def needs_build():
-    if not os.path.exists(LIB):
+def needs_build(lib=LIB):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "codenerf_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
+def build(force=False, verbose=False, trace=False):
+    lib = LIB_TRACE if trace else LIB
+    if not force and not needs_build(lib):
+        return lib
     objs = []
     procs = []
-    os.makedirs(os.path.join(HERE, "..", "build"), exist_ok=True)
+    obj_dir = os.path.join(HERE, "..", "build", "trace" if trace else "")
+    os.makedirs(obj_dir, exist_ok=True)
+    extra = os.environ.get("CNB_NVCC_EXTRA", "").split() + (["-DCNB_TRACE"] if trace else [])
     for s in SOURCES:
-        o = os.path.join(HERE, "..", "build", s.replace(".cu", ".o"))
-        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-               "-Xcompiler", "-fPIC", "-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, s), "-o", o]
-        cmd[1:1] = os.environ.get("CNB_NVCC_EXTRA", "").split()      # e.g. -DCNB_TRACE (debug builds)
+        o = os.path.join(obj_dir, s.replace(".cu", ".o"))
+        cmd = [_nvcc()] + extra + NVCC_FLAGS + ["-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     failed = False
@@ -47,10 +54,10 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", lib] + objs + ["-lcudart"]
     subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))

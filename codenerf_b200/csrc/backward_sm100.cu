@@ -62,13 +62,18 @@ struct BwdParams {
     const float *xyz, *viewdir;
     int64_t S, row_offset;          // rows of this launch; global row of its first row (codes, rays)
     const float *d_sigmas, *d_rgbs; // seeds, launch-relative rows: [S], [S,3]
-    uint32_t* mask_scratch;         // [grid][2][n_layers][8][128]
+    uint32_t* mask_scratch;         // [grid][2 groups][1 + lookahead][n_layers][8][128]
     float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l
     int stash;                      // 1: stream operand tiles + dspre to HBM (training)
     uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
     uint8_t *stashA, *stashD;
     float* dspre;                   // [S] d(loss)/d(sigma pre-activation)
-    // fused compositing (+ loss) when every tile holds whole rays (128 % N == 0): the seeds are made in-kernel
+    // Work is handed out in UNITS of `unit_tiles` consecutive tiles that hold whole rays (unit_tiles * 128 is a
+    // multiple of N).  With rays straddling tiles (unit_tiles > 1, e.g. N = 96: 4 rays = 3 tiles) a tile's backward
+    // chain starts one tile late (`lookahead` = 1): F(0) F(1) B(0) F(2) B(1) ... B(U-1), so every ray touching the
+    // tile has been composited; ReLU masks and the sample ring are double-buffered by tile parity.
+    int unit_tiles, lookahead;
+    // fused compositing (+ loss): the seeds are made in-kernel
     int fuse_comp;                  // 0: seeds from d_sigmas / d_rgbs; 1: from d_rgb_rays / d_depth_rays; 2: from target (L2)
     int white_bg;
     int64_t n_rays_total;
@@ -91,13 +96,14 @@ __device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) {
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
-// Forward compositing, loss seed and reverse-mode compositing of ONE ray by one warp, on the tile's
-// per-sample (sigma, r, g, b) in shared memory -- reference src/utils.py:34-47 and its autograd, the L2
-// seed of src/trainer.py:75.  N <= 128 (up to 4 samples per lane).  Writes per-sample seeds to `seed`.
-__device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, const float4* smp, float4* seed, int64_t gray,
-                                                  int lane) {
+// Forward compositing, loss seed and reverse-mode compositing of ONE ray by one warp -- reference
+// src/utils.py:34-47 and its autograd, the L2 seed of src/trainer.py:75.  The ray's per-sample (sigma, r, g, b) sit
+// in the group's 256-entry sample ring (two tiles) at ring[(start + k) & 255], k < N <= 128, so a ray may straddle
+// two tiles; the per-sample seeds (d sigma, d r, d g, d b) overwrite them in place.  Any N in [1, 128]: lane l owns
+// samples [l * per, l * per + per) with per = ceil(N / 32); samples past N are identities of both scans.
+__device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, float4* ring, int start, int64_t gray, int lane) {
     const int N = p.rs.N;
-    const int per = N >> 5;          // N in {32, 64, 128}
+    const int per = (N + 31) >> 5;
     const int i0 = lane * per;
     const bool live = gray < p.n_rays_total;
     const int64_t seg = (live ? gray : 0) / p.rs.rays_per_segment;
@@ -107,9 +113,10 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, const float4*
     float tl = 1.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        if (j < per) {
-            const int i = i0 + j;
-            s[j] = smp[i];
+        alpha[j] = 0.f; tt[j] = 1.f; dl[j] = 0.f; ex[j] = 0.f; zz[j] = 0.f; s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = i0 + j;
+        if (j < per && i < N) {
+            s[j] = ring[(start + i) & 255];
             zz[j] = __ldg(z + i);
             dl[j] = (i + 1 < N) ? (__ldg(z + i + 1) - zz[j]) : 1e10f;
             ex[j] = expf(-s[j].x * dl[j]);
@@ -129,12 +136,10 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, const float4*
         float T = T0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            if (j < per) {
-                Tj[j] = T;
-                const float w = alpha[j] * T;
-                cr += w * s[j].y; cg += w * s[j].z; cb += w * s[j].w; dep += w * zz[j]; ws += w;
-                T *= tt[j];
-            }
+            Tj[j] = T;
+            const float w = alpha[j] * T;
+            cr += w * s[j].y; cg += w * s[j].z; cb += w * s[j].w; dep += w * zz[j]; ws += w;
+            T *= tt[j];
         }
     }
     cr = warp_sum_f(cr); cg = warp_sum_f(cg); cb = warp_sum_f(cb); dep = warp_sum_f(dep); ws = warp_sum_f(ws);
@@ -164,11 +169,9 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, const float4*
     float A = 1.f, Bc = 0.f;
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
-        if (j < per) {
-            gsm[j] = gr * (s[j].y - bg) + gg * (s[j].z - bg) + gb * (s[j].w - bg) + gd * zz[j];
-            Bc = gsm[j] * alpha[j] + tt[j] * Bc;
-            A = tt[j] * A;
-        }
+        gsm[j] = gr * (s[j].y - bg) + gg * (s[j].z - bg) + gb * (s[j].w - bg) + gd * zz[j];
+        Bc = gsm[j] * alpha[j] + tt[j] * Bc;
+        A = tt[j] * A;
     }
     float sA = A, sB = Bc;
 #pragma unroll
@@ -181,12 +184,10 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, const float4*
     if (lane == 31) aT_next = 0.f;
 #pragma unroll
     for (int j = 3; j >= 0; --j) {
-        if (j < per) {
-            const float w = alpha[j] * Tj[j];
-            const float a_alpha = (gsm[j] - aT_next) * Tj[j];
-            seed[i0 + j] = make_float4(a_alpha * dl[j] * ex[j], w * gr, w * gg, w * gb);
-            aT_next = gsm[j] * alpha[j] + aT_next * tt[j];
-        }
+        const float w = alpha[j] * Tj[j];
+        const float a_alpha = (gsm[j] - aT_next) * Tj[j];
+        if (j < per && i0 + j < N) ring[(start + i0 + j) & 255] = make_float4(a_alpha * dl[j] * ex[j], w * gr, w * gg, w * gb);
+        aT_next = gsm[j] * alpha[j] + aT_next * tt[j];
     }
 }
 
@@ -244,11 +245,16 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
 }
 
 // MC > 1: clusters of MC CTAs share one multicast weight stream (see produce_stages); every CTA of a cluster runs
-// the same number of tile slots, the surplus ones as phantom tiles (all rows invalid, nothing written).
+// the same number of unit slots, the surplus ones as phantom units (all rows invalid, nothing written).
 // CG = 2: CTA pairs (tcgen05 cta_group::2, M = 256 = one tile of each CTA): every CTA streams half of each weight
-// chunk and reads half of the B operand -- 128 KB less shared-memory traffic per tile and GEMM, which is what bounds
-// this kernel; the leader CTA issues the MMAs, the epilogue warps of both CTAs arrive on its
-// a_ready barriers, accumulator / ring-slot commits are multicast to both.
+// chunk and reads half of the B operand; the leader CTA issues the MMAs, the epilogue warps of both CTAs arrive on
+// its a_ready barriers, accumulator / ring-slot commits are multicast to both.
+//
+// Schedule of one compute group over one unit of U tiles (LA = lookahead, 0 or 1):
+//     for i in [0, U + LA):   if (i < U) F(i);   if (i >= LA) B(i - LA);
+// F(t) = positional encodings + the nl forward GEMMs of tile t (+ compositing of every ray whose last sample lies
+// in t), B(t) = step 0 + the ns - 1 input-gradient GEMMs of tile t.  The producer, the MMA issuer and the auxiliary
+// warps walk the same sequence; the two groups' GEMMs alternate op by op.
 template <int MC, int CG = 1>
 __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constant__ BwdParams p) {
     static_assert(CG == 1 || MC == 1, "pairs and multicast clusters are alternatives");
@@ -265,23 +271,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     uint64_t* aux_ready = acc_full + 2;          // [2] a tile operand was (re)written (every phase)
     uint64_t* buf_free = aux_ready + 2;          // [2] aux warp finished reading the operand buffer
     uint32_t* tmem_slot = (uint32_t*)(buf_free + 2);
-    float4* sSamp = (float4*)(tmem_slot + 4);      // [2][128] per-sample (sigma, r, g, b) of the group's tile
-    float4* sSeed = sSamp + 2 * kTileRows;         // [2][128] per-sample (d sigma, d r, d g, d b)
-    float* sBias = (float*)(sSeed + 2 * kTileRows);  // [2 groups][2 buffers][256] bias row of the layer being drained
+    float4* sRing = (float4*)(tmem_slot + 4);      // [2 groups][256] per-sample (sigma, r, g, b), then seeds: two tiles per group
+    float* sBias = (float*)(sRing + 4 * kTileRows);  // [2 groups][2 buffers][256] bias row of the layer being drained
     float* sWsig = sBias + 4 * kW;                  // [256] sigma-head weights
     float* sWrgb = sWsig + kW;                      // [3][128] rgb.2 weights
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = p.n_layers, ns = p.n_steps;
-    const int n_ops = nl + ns - 1;               // MMA operations per tile
+    const int U = p.unit_tiles, LA = p.lookahead;
 
     const int64_t tiles = (p.S + kTileRows - 1) / kTileRows;
-    const int64_t tbase = tiles / gridDim.x, trem = tiles % gridDim.x;
-    const int64_t tile0 = (int64_t)blockIdx.x * tbase + min((int64_t)blockIdx.x, trem);
-    const int T_own = (int)(tbase + ((int64_t)blockIdx.x < trem ? 1 : 0));
+    const int64_t units = (tiles + U - 1) / U;
+    const int64_t ubase = units / gridDim.x, urem = units % gridDim.x;
+    const int64_t unit0 = (int64_t)blockIdx.x * ubase + min((int64_t)blockIdx.x, urem);
+    const int UN_own = (int)(ubase + ((int64_t)blockIdx.x < urem ? 1 : 0));
     const uint32_t rank = kCluster > 1 ? umma::cluster_ctarank() : 0u;
-    const int T = kCluster > 1 ? (int)(tbase + ((int64_t)(blockIdx.x - rank) < trem ? 1 : 0)) : T_own;   // cluster-uniform
-    const int rounds = (T + 1) >> 1;
+    const int UN = kCluster > 1 ? (int)(ubase + ((int64_t)(blockIdx.x - rank) < urem ? 1 : 0)) : UN_own;   // cluster-uniform
+    const int rounds = (UN + 1) >> 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kNumStages; ++i) { umma::mbar_init(&w_full[i], 1); umma::mbar_init(&w_empty[i], MC); }
@@ -308,45 +314,57 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         int stage = 0; uint32_t ph = 0;
         const uint64_t pol_w = p.stash ? umma::l2_policy_evict_last() : 0ull;   // the stash stream must not evict the weights
         for (int r = 0; r < rounds; ++r)
-            for (int op = 0; op < n_ops; ++op)
-                for (int g = 0; g < 2; ++g) {
-                    if (2 * r + g >= T) continue;
-                    if (op < nl) {
-                        const FwdLayer& L = p.layers[op];
-                        const int n_dir = L.has_dir ? L.n_halves : 0;
-                        if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
-                        else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
-                    } else {
-                        const BwdStep& B = p.steps[op - nl + 1];
-                        if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph);
-                        else produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
-                    }
-                }
+            for (int i = 0; i < U + LA; ++i) {
+                if (i < U)
+                    for (int op = 0; op < nl; ++op)
+                        for (int g = 0; g < 2; ++g) {
+                            if (2 * r + g >= UN) continue;
+                            const FwdLayer& L = p.layers[op];
+                            const int n_dir = L.has_dir ? L.n_halves : 0;
+                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
+                            else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
+                        }
+                if (i >= LA)
+                    for (int s = 1; s < ns; ++s)
+                        for (int g = 0; g < 2; ++g) {
+                            if (2 * r + g >= UN) continue;
+                            const BwdStep& B = p.steps[s];
+                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph);
+                            else produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
+                        }
+            }
     } else if (warp == 1) {
         // ===== MMA issuer =====
         int stage = 0; uint32_t ph = 0;
+        uint32_t cnt[2] = {0u, 0u};               // operands consumed so far per group (a_ready parity)
         CNB_TR_DECL(tr_wa); CNB_TR_DECL(tr_ww); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
+        auto issue = [&](int g, int n_kchunks, int n_halves, int has_dir, int ev_op) {
+            const uint32_t par = cnt[g] & 1u; ++cnt[g];
+            if (CG == 2 && rank != 0) return;            // the partner CTA issues no MMAs
+            if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], par));
+            else CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], par));
+            CNB_EV(lane, 0, (1 << 12) | (g << 8) | ev_op);          // operands ready, issue starts
+            umma::tc_fence_after();
+            if (CG == 2)
+                issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                                n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
+            else
+                issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                               n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
+            CNB_EV(lane, 0, (2 << 12) | (g << 8) | ev_op);          // all MMAs of the op issued
+        };
         for (int r = 0; r < rounds; ++r)
-            for (int op = 0; op < n_ops; ++op)
-                for (int g = 0; g < 2; ++g) {
-                    if (2 * r + g >= T) continue;
-                    int n_kchunks, n_halves, has_dir;
-                    if (op < nl) { n_kchunks = p.layers[op].n_kchunks; n_halves = p.layers[op].n_halves; has_dir = p.layers[op].has_dir; }
-                    else { n_kchunks = p.steps[op - nl + 1].n_kchunks; n_halves = 2; has_dir = 0; }
-                    if (CG == 2 && rank != 0) continue;          // the partner CTA issues no MMAs
-                    if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
-                    else CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], (uint32_t)(r * n_ops + op) & 1u));
-                    CNB_EV(lane, 0, (1 << 12) | (g << 8) | op);          // operands ready, issue starts
-                    umma::tc_fence_after();
-                    if (CG == 2)
-                        issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
-                                        n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
-                    else
-                        issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
-                                       n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
-                    CNB_EV(lane, 0, (2 << 12) | (g << 8) | op);          // all MMAs of the op issued
-                }
+            for (int i = 0; i < U + LA; ++i) {
+                if (i < U)
+                    for (int op = 0; op < nl; ++op)
+                        for (int g = 0; g < 2; ++g)
+                            if (2 * r + g < UN) issue(g, p.layers[op].n_kchunks, p.layers[op].n_halves, p.layers[op].has_dir, op);
+                if (i >= LA)
+                    for (int s = 1; s < ns; ++s)
+                        for (int g = 0; g < 2; ++g)
+                            if (2 * r + g < UN) issue(g, p.steps[s].n_kchunks, 2, 0, nl + s - 1);
+            }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(0, tr_wa); CNB_TR_FLUSH(1, tr_ww); CNB_TR_FLUSH(2, tr_tot);
     } else {
@@ -355,59 +373,72 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const uint8_t* sA = sA0 + g * kATile;
         uint32_t ap = 0;
         const uint64_t pol_stream = umma::l2_policy_evict_first();   // the stash is written once and read by a later kernel
-        const int n_phases = nl + 1 + ns;
         CNB_TR_DECL(tr_wx); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
-        for (int r = 0; r < rounds; ++r) {
-            const int t = 2 * r + g;
-            if (t >= T) break;
-            const bool phantom = t >= T_own;
-            const bool stash = p.stash && !phantom;
-            const int64_t tile = tile0 + t;
-            int64_t code = 0;
-            if (p.n_codes > 1) { code = (p.row_offset + tile * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
-            for (int phs = 0; phs < n_phases; ++phs) {
-                if (phs == nl && !p.stash) continue;      // the rgb.2 input is only written for the stash
-                CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
-                int blocks = 0, out_layer = -1;
-                uint8_t* dst = nullptr;
-                if (phs == 0) { blocks = 1; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[0]; }
-                else if (phs < nl) { blocks = 4; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[phs]; }
-                else if (phs == nl) { blocks = 2; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[nl]; }
-                else {
-                    const BwdStep& B = p.steps[phs - nl - 1];
-                    blocks = B.out_blocks; out_layer = B.out_layer;
-                    dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
-                }
-                if (stash) {
-                    // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
-                    // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
-                    const uint32_t piece = (uint32_t)blocks * (kABlock / 32);
-                    umma::bulk_s2g_hint(dst + (size_t)lane * piece, sA + (size_t)lane * piece, piece, pol_stream);
-                    if (phs == 0)
-                        umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot + lane * (kDirBlock / 32),
-                                            sA + 4 * kABlock + lane * (kDirBlock / 32), kDirBlock / 32, pol_stream);
-                    umma::bulk_commit();
-                }
-                if (!phantom && out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
-                    const int blk = lane >> 3, chunk = lane & 7;
-                    float acc[8];
+        // one operand-buffer phase: wait for the write, stash it and / or reduce its column sums, release the buffer
+        auto phase = [&](int64_t tile, bool live, int phs) {
+            CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
+            const bool stash = p.stash && live;
+            int blocks = 0, out_layer = -1;
+            uint8_t* dst = nullptr;
+            if (phs == 0) { blocks = 1; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[0]; }
+            else if (phs < nl) { blocks = 4; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[phs]; }
+            else if (phs == nl) { blocks = 2; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[nl]; }
+            else {
+                const BwdStep& B = p.steps[phs - nl - 1];
+                blocks = B.out_blocks; out_layer = B.out_layer;
+                dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
+            }
+            if (stash) {
+                // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
+                // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
+                const uint32_t piece = (uint32_t)blocks * (kABlock / 32);
+                umma::bulk_s2g_hint(dst + (size_t)lane * piece, sA + (size_t)lane * piece, piece, pol_stream);
+                if (phs == 0)
+                    umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot + lane * (kDirBlock / 32),
+                                        sA + 4 * kABlock + lane * (kDirBlock / 32), kDirBlock / 32, pol_stream);
+                umma::bulk_commit();
+            }
+            if (live && out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
+                int64_t code = 0;
+                if (p.n_codes > 1) { code = (p.row_offset + tile * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+                const int blk = lane >> 3, chunk = lane & 7;
+                float acc[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                    const uint8_t* base = sA + blk * kABlock;
+                for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+                const uint8_t* base = sA + blk * kABlock;
 #pragma unroll 4
-                    for (int rr = 0; rr < kTileRows; ++rr) {
-                        const uint4 w = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-                        acc[0] += bf_lo(w.x); acc[1] += bf_hi(w.x); acc[2] += bf_lo(w.y); acc[3] += bf_hi(w.y);
-                        acc[4] += bf_lo(w.z); acc[5] += bf_hi(w.z); acc[6] += bf_lo(w.w); acc[7] += bf_hi(w.w);
-                    }
-                    float* out = p.colsum + ((size_t)code * nl + out_layer) * kW + blk * 64 + chunk * 8;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
+                for (int rr = 0; rr < kTileRows; ++rr) {
+                    const uint4 w = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                    acc[0] += bf_lo(w.x); acc[1] += bf_hi(w.x); acc[2] += bf_lo(w.y); acc[3] += bf_hi(w.y);
+                    acc[4] += bf_lo(w.z); acc[5] += bf_hi(w.z); acc[6] += bf_lo(w.w); acc[7] += bf_hi(w.w);
                 }
-                if (stash) umma::bulk_wait_read_all();
-                __syncwarp();
-                if (lane == 0) umma::mbar_arrive(&buf_free[g]);
+                float* out = p.colsum + ((size_t)code * nl + out_layer) * kW + blk * 64 + chunk * 8;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
+            }
+            if (stash) umma::bulk_wait_read_all();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(&buf_free[g]);
+        };
+        for (int r = 0; r < rounds; ++r) {
+            const int u = 2 * r + g;
+            if (u >= UN) break;
+            const int64_t utile0 = (unit0 + u) * U;
+            for (int i = 0; i < U + LA; ++i) {
+                if (i < U) {
+                    const int64_t tile = utile0 + i;
+                    const bool live = u < UN_own && tile < tiles;
+                    for (int phs = 0; phs <= nl; ++phs) {
+                        if (phs == nl && !p.stash) continue;      // the rgb.2 input is only written for the stash
+                        phase(tile, live, phs);
+                    }
+                }
+                if (i >= LA) {
+                    const int64_t tile = utile0 + i - LA;
+                    const bool live = u < UN_own && tile < tiles;
+                    for (int s = 0; s < ns; ++s) phase(tile, live, nl + 1 + s);
+                }
             }
         }
         if (p.stash) umma::bulk_wait_all();
@@ -429,9 +460,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const uint64_t pol_keep = umma::l2_policy_evict_last();   // ReLU masks: written now, re-read ~50 us later
         uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
         uint32_t opc = 0;     // accumulator phases consumed
-        uint32_t* mscr = p.mask_scratch + ((size_t)(blockIdx.x * 2 + g) * nl) * 8 * kTileRows + row;
+        const size_t mask_set = (size_t)nl * 8 * kTileRows;      // words of one tile's ReLU masks
+        uint32_t* mscr = p.mask_scratch + (size_t)(blockIdx.x * 2 + g) * (1 + LA) * mask_set + row;
         const int tg = (warp & 3) * 32 + lane;           // thread index inside the group
         float* sB = sBias + g * 2 * kW;
+        float4* ring = sRing + g * 2 * kTileRows;
         uint32_t bsel = 0;                               // staging buffer of the next layer (alternates)
 
         CNB_TR_DECL(tr_wbuf); CNB_TR_DECL(tr_wacc_f); CNB_TR_DECL(tr_epi_f); CNB_TR_DECL(tr_mid); CNB_TR_DECL(tr_wacc_b);
@@ -449,11 +482,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             ++wp;
         };
 
-        // rays / samples / positional encodings of tile slot t of this group, as packed bf16 rows in registers
-        auto prepare_tile = [&](int t, PeRow& pe) {
-            const bool ph = t >= T_own;
-            const int64_t lr = (tile0 + t) * kTileRows + row;
-            const bool ok = !ph && t < T && lr < p.S;
+        // rays / samples / positional encodings of one tile (tile < 0: none), as packed bf16 rows in registers
+        auto prepare_tile = [&](int64_t tile, PeRow& pe) {
+            const int64_t lr = tile * kTileRows + row;
+            const bool ok = tile >= 0 && lr < p.S;
             float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
             if (ok) {
                 if (p.mode == 0) {
@@ -474,148 +506,182 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             pe_compute_xyz(pos, ok, pe.x);
             pe_compute_dir(dir, ok, pe.d);
         };
+        // first tile of unit slot u of this group (-1: none; phantom units encode all-zero rows)
+        auto unit_tile0 = [&](int u) -> int64_t { return (u < UN && u < UN_own) ? (unit0 + u) * U : (int64_t)-1; };
         PeRow pe;
-        if (g < T) prepare_tile(g, pe);
+        bool pe_ready = false;
+        if (g < UN) { prepare_tile(unit_tile0(g), pe); pe_ready = true; }
 
         for (int r = 0; r < rounds; ++r) {
-            const int t = 2 * r + g;
-            if (t >= T) break;
-            const bool phantom = t >= T_own;
-            const long long tr_e0 = CNB_TR_NOW();
-            const int64_t lrow = (tile0 + t) * kTileRows + row;      // launch-relative row
-            const bool valid = !phantom && lrow < p.S;
-            float ds = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
-            if (valid && !p.fuse_comp) {
-                ds = __ldg(p.d_sigmas + lrow);
-                dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
-            }
-            int64_t code = 0;
-            if (p.n_codes > 1) { code = (p.row_offset + (tile0 + t) * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+            const int u = 2 * r + g;
+            if (u >= UN) break;
+            const bool phantom = u >= UN_own;
+            const int64_t utile0 = (unit0 + u) * U;
+            float x_even = 0.f, x_odd = 0.f;       // sigma pre-activation of this row in the unit's even / odd tiles
+            for (int i = 0; i < U + LA; ++i) {
+                uint32_t mlast4[4];
+                if (i < U) {
+                    // =================== F(i): forward chain of tile utile0 + i ===================
+                    const int64_t tile = utile0 + i;
+                    const long long tr_e0 = CNB_TR_NOW();
+                    int64_t code = 0;
+                    if (p.n_codes > 1) { code = (p.row_offset + tile * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
+                    if (!pe_ready) prepare_tile(phantom ? (int64_t)-1 : tile, pe);
+                    pe_ready = false;
+                    // ---- phase F0: positional encodings (normally computed during the previous tile's backward chain) ----
+                    wait_buf_free();
+                    pe_store_xyz(pe.x, sA, row);
+                    pe_store_dir(pe.d, sA + 4 * kABlock, row);
+                    publish(true);
+                    if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (6 << 12) | (g << 8));               // encodings stored: tile starts
+                    tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
-            // ---- phase F0: positional encodings (computed during the previous tile's backward chain) ----
-            wait_buf_free();
-            pe_store_xyz(pe.x, sA, row);
-            pe_store_dir(pe.d, sA + 4 * kABlock, row);
-            publish(true);
-            if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (6 << 12) | (g << 8));               // encodings stored: tile starts
-            tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
-
-            // ---- forward chain (recompute) ----
-            HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, pol_keep};
-            for (int l = 0; l < nl; ++l) {
-                const FwdLayer& L = p.layers[l];
-                const float* bias_g = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
-                float2 bias2 = make_float2(0.f, 0.f);
-                if (2 * tg < L.n_halves * 128) bias2 = __ldg(reinterpret_cast<const float2*>(bias_g) + tg);   // in flight during the wait
-                CNB_TR(tr_wacc_f, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
-                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | l);      // accumulator visible: epilogue starts
-                const long long tr_p0 = CNB_TR_NOW();
-                umma::tc_fence_after();
-                const bool last = (l + 1 == nl);
-                const bool store = !last || p.stash;
-                if (store) wait_buf_free();
-                // the layer's bias row goes through shared memory: 2 floats per thread, then LDS broadcasts
-                float* sb = sB + bsel * kW; bsel ^= 1u;
-                if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
-                const uint32_t tok = bar_sync_token(1 + g, 128);
-                const float* bias = smem_fptr(sb, tok);
-                const float* wsig_s = smem_fptr(sWsig, tok);     // per-layer token: the staged rows are read inside this layer
-                const float* wrgb_s = smem_fptr(sWrgb, tok);     // (an invariant address would be hoisted out of the tile loop)
-                uint32_t* ml = mscr + (size_t)l * 8 * kTileRows;
-                if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                else if (p.fuse_comp) {
-                    if (store) fwd_epilogue_layer<4, 2, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                    else fwd_epilogue_layer<4, 2, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                }
-                else if (store) fwd_epilogue_layer<4, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                else fwd_epilogue_layer<4, 0, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                if (store) publish(!last);
-                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | l);      // epilogue done, operand published
-                tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
-            }
-            const long long tr_m0 = CNB_TR_NOW();
-            // ReLU bit words of rgb.0 for step 0: fetched now, used after the compositing (L2 latency overlapped)
-            uint32_t mlast4[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) mlast4[c] = umma::ld_global_hint(mscr + ((size_t)(nl - 1) * 8 + c) * kTileRows, pol_keep);
-            float sig_pre;
-            { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
-            const float x = sig_pre + __ldg(p.b_sigma);
-            if (p.fuse_comp) {
-                // per-ray compositing, loss seed and compositing backward inside the tile
-                float a0, a1, cr, cg, cb;
-                unpk2(hacc.r2, a0, a1); cr = a0 + a1 + __ldg(p.b_rgb2 + 0);
-                unpk2(hacc.g2, a0, a1); cg = a0 + a1 + __ldg(p.b_rgb2 + 1);
-                unpk2(hacc.b2, a0, a1); cb = a0 + a1 + __ldg(p.b_rgb2 + 2);
-                float4* samp = sSamp + g * kTileRows;
-                float4* seed = sSeed + g * kTileRows;
-                samp[row] = make_float4(cnb_softplus(x), cr, cg, cb);
-                umma::named_bar_sync(1 + g, 128);
-                const int rays_in_tile = kTileRows / N;
-                const int64_t ray_base = phantom ? p.n_rays_total : (p.row_offset + (tile0 + t) * kTileRows) / N;
-                for (int k = warp & 3; k < rays_in_tile; k += 4)
-                    composite_fwd_bwd(p, samp + k * N, seed + k * N, ray_base + k, lane);
-                umma::named_bar_sync(1 + g, 128);
-                const float4 sd = seed[row];
-                ds = sd.x; dcr = sd.y; dcg = sd.z; dcb = sd.w;
-            }
-            const float ex = expf(x);
-            const float dspre = x > 20.f ? ds : ds * ex / (ex + 1.f);      // softplus backward (ATen form)
-            if (p.stash && valid) {
-                p.dspre[lrow] = dspre;
-                if (p.fuse_comp) { p.drgb_out[lrow * 3] = dcr; p.drgb_out[lrow * 3 + 1] = dcg; p.drgb_out[lrow * 3 + 2] = dcb; }
-            }
-
-            // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
-            wait_buf_free();
-            {
-                const float* wrgb_s = smem_fptr(sWrgb, order_token());
-                const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
-#pragma unroll
-                for (int c8 = 0; c8 < 16; ++c8) {
-                    const uint32_t mlast = mlast4[c8 >> 2];
-                    const int col = c8 * 8;
-                    uint32_t w[4];
-#pragma unroll
-                    for (int hh = 0; hh < 2; ++hh) {
-                        const float4 w0 = ld_vec4<true>(wrgb_s + col + hh * 4);
-                        const float4 w1 = ld_vec4<true>(wrgb_s + (kW / 2) + col + hh * 4);
-                        const float4 w2 = ld_vec4<true>(wrgb_s + kW + col + hh * 4);
-                        uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
-                        uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
-                        float f0, f1, f2, f3; unpk2(v0, f0, f1); unpk2(v1, f2, f3);
-                        const int pos = (col & 31) + hh * 4;
-                        f0 = (mlast & (0x80000000u >> (pos + 0))) ? f0 : 0.f; f1 = (mlast & (0x80000000u >> (pos + 1))) ? f1 : 0.f;
-                        f2 = (mlast & (0x80000000u >> (pos + 2))) ? f2 : 0.f; f3 = (mlast & (0x80000000u >> (pos + 3))) ? f3 : 0.f;
-                        w[hh * 2 + 0] = cvt_bf16x2<false>(pk2f(f0, f1)); w[hh * 2 + 1] = cvt_bf16x2<false>(pk2f(f2, f3));
+                    uint32_t* mset = mscr + (size_t)(LA ? (i & 1) : 0) * mask_set;
+                    HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, pol_keep};
+                    for (int l = 0; l < nl; ++l) {
+                        const FwdLayer& L = p.layers[l];
+                        const float* bias_g = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
+                        float2 bias2 = make_float2(0.f, 0.f);
+                        if (2 * tg < L.n_halves * 128) bias2 = __ldg(reinterpret_cast<const float2*>(bias_g) + tg);   // in flight during the wait
+                        CNB_TR(tr_wacc_f, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                        if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | l);      // accumulator visible: epilogue starts
+                        const long long tr_p0 = CNB_TR_NOW();
+                        umma::tc_fence_after();
+                        const bool last = (l + 1 == nl);
+                        const bool store = !last || p.stash;
+                        if (store) wait_buf_free();
+                        // the layer's bias row goes through shared memory: 2 floats per thread, then LDS broadcasts
+                        float* sb = sB + bsel * kW; bsel ^= 1u;
+                        if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
+                        const uint32_t tok = bar_sync_token(1 + g, 128);
+                        const float* bias = smem_fptr(sb, tok);
+                        const float* wsig_s = smem_fptr(sWsig, tok);     // per-layer token: the staged rows are read inside this layer
+                        const float* wrgb_s = smem_fptr(sWrgb, tok);     // (an invariant address would be hoisted out of the tile loop)
+                        uint32_t* ml = mset + (size_t)l * 8 * kTileRows;
+                        if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                        else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                        else if (p.fuse_comp) {
+                            if (store) fwd_epilogue_layer<4, 2, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                            else fwd_epilogue_layer<4, 2, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                        }
+                        else if (store) fwd_epilogue_layer<4, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                        else fwd_epilogue_layer<4, 0, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                        if (store) publish(!last);
+                        if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | l);      // epilogue done, operand published
+                        tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
                     }
-                    if (c8 < 8) st_shared_v4_off<0>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
-                    else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                    const long long tr_m0 = CNB_TR_NOW();
+                    // ReLU bit words of rgb.0 of the tile whose backward chain runs next: fetched now, used after the
+                    // compositing (L2 latency overlapped)
+                    if (i >= LA) {
+                        const uint32_t* mb = mscr + (size_t)(LA ? ((i - LA) & 1) : 0) * mask_set;
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) mlast4[c] = umma::ld_global_hint(mb + ((size_t)(nl - 1) * 8 + c) * kTileRows, pol_keep);
+                    }
+                    float sig_pre;
+                    { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
+                    const float x = sig_pre + __ldg(p.b_sigma);
+                    if (i & 1) x_odd = x; else x_even = x;
+                    if (p.fuse_comp) {
+                        // per-ray compositing, loss seed and compositing backward of every ray that ends in this tile
+                        float a0, a1, cr, cg, cb;
+                        unpk2(hacc.r2, a0, a1); cr = a0 + a1 + __ldg(p.b_rgb2 + 0);
+                        unpk2(hacc.g2, a0, a1); cg = a0 + a1 + __ldg(p.b_rgb2 + 1);
+                        unpk2(hacc.b2, a0, a1); cb = a0 + a1 + __ldg(p.b_rgb2 + 2);
+                        ring[((i & 1) << 7) + row] = make_float4(cnb_softplus(x), cr, cg, cb);
+                        umma::named_bar_sync(1 + g, 128);
+                        const int j_lo = (i * kTileRows) / N, j_hi = ((i + 1) * kTileRows) / N;      // rays of the unit ending in tile i
+                        const int64_t ray_unit0 = phantom ? p.n_rays_total : (p.row_offset + utile0 * kTileRows) / N;
+                        for (int j = j_lo + (warp & 3); j < j_hi; j += 4)
+                            composite_fwd_bwd(p, ring, (j * N) & 255, phantom ? p.n_rays_total : ray_unit0 + j, lane);
+                        umma::named_bar_sync(1 + g, 128);
+                    }
+                    tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
+                } else {
+                    const uint32_t* mb = mscr + (size_t)((i - LA) & 1) * mask_set;       // i == U: only with lookahead
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) mlast4[c] = umma::ld_global_hint(mb + ((size_t)(nl - 1) * 8 + c) * kTileRows, pol_keep);
                 }
-            }
-            publish(ns > 1);
-            if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (5 << 12) | (g << 8) | nl);         // compositing + step 0 done
-            tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
+                if (i >= LA) {
+                    // =================== B(i - LA): input-gradient chain of tile utile0 + i - LA ===================
+                    const int ib = i - LA;
+                    const int64_t tile = utile0 + ib;
+                    const long long tr_m0 = CNB_TR_NOW();
+                    const int64_t lrow = tile * kTileRows + row;      // launch-relative row
+                    const bool valid = !phantom && lrow < p.S;
+                    float ds = 0.f, dcr = 0.f, dcg = 0.f, dcb = 0.f;
+                    if (p.fuse_comp) {
+                        const float4 sd = ring[((ib & 1) << 7) + row];
+                        ds = sd.x; dcr = sd.y; dcg = sd.z; dcb = sd.w;
+                    } else if (valid) {
+                        ds = __ldg(p.d_sigmas + lrow);
+                        dcr = __ldg(p.d_rgbs + lrow * 3 + 0); dcg = __ldg(p.d_rgbs + lrow * 3 + 1); dcb = __ldg(p.d_rgbs + lrow * 3 + 2);
+                    }
+                    const float x = (ib & 1) ? x_odd : x_even;
+                    const float ex = expf(x);
+                    const float dspre = x > 20.f ? ds : ds * ex / (ex + 1.f);      // softplus backward (ATen form)
+                    if (p.stash && valid) {
+                        p.dspre[lrow] = dspre;
+                        if (p.fuse_comp) { p.drgb_out[lrow * 3] = dcr; p.drgb_out[lrow * 3 + 1] = dcg; p.drgb_out[lrow * 3 + 2] = dcb; }
+                    }
+                    const uint32_t* mset = mscr + (size_t)(LA ? (ib & 1) : 0) * mask_set;
 
-            // ---- input-gradient chain ----
-            const uint64_t dsp2 = pk2f(dspre, dspre);
-            for (int s = 1; s < ns; ++s) {
-                const BwdStep& B = p.steps[s];
-                if (s == (ns > 3 ? 3 : 1)) prepare_tile(t + 2, pe);   // next tile of this group: its PE is computed inside a long (K = 256) MMA wait
-                CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
-                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | (nl + s - 1));
-                const long long tr_b0 = CNB_TR_NOW();
-                umma::tc_fence_after();
-                wait_buf_free();
-                const uint32_t* ml = mscr + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
-                const float* wsig_s = smem_fptr(sWsig, order_token());
-                if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
-                else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
-                else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
-                publish(s + 1 < ns);
-                if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | (nl + s - 1));
-                tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
+                    // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
+                    wait_buf_free();
+                    {
+                        const float* wrgb_s = smem_fptr(sWrgb, order_token());
+                        const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
+#pragma unroll
+                        for (int c8 = 0; c8 < 16; ++c8) {
+                            const uint32_t mlast = mlast4[c8 >> 2];
+                            const int col = c8 * 8;
+                            uint32_t w[4];
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {
+                                const float4 w0 = ld_vec4<true>(wrgb_s + col + hh * 4);
+                                const float4 w1 = ld_vec4<true>(wrgb_s + (kW / 2) + col + hh * 4);
+                                const float4 w2 = ld_vec4<true>(wrgb_s + kW + col + hh * 4);
+                                uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
+                                uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
+                                float f0, f1, f2, f3; unpk2(v0, f0, f1); unpk2(v1, f2, f3);
+                                const int pos = (col & 31) + hh * 4;
+                                f0 = (mlast & (0x80000000u >> (pos + 0))) ? f0 : 0.f; f1 = (mlast & (0x80000000u >> (pos + 1))) ? f1 : 0.f;
+                                f2 = (mlast & (0x80000000u >> (pos + 2))) ? f2 : 0.f; f3 = (mlast & (0x80000000u >> (pos + 3))) ? f3 : 0.f;
+                                w[hh * 2 + 0] = cvt_bf16x2<false>(pk2f(f0, f1)); w[hh * 2 + 1] = cvt_bf16x2<false>(pk2f(f2, f3));
+                            }
+                            if (c8 < 8) st_shared_v4_off<0>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                            else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                        }
+                    }
+                    publish(ns > 1);
+                    if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (5 << 12) | (g << 8) | nl);         // compositing + step 0 done
+                    tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
+
+                    // the tile whose forward chain this group runs next: its encodings are computed inside a long MMA wait
+                    int64_t next_tile = -2;                      // -2: nothing follows
+                    if (i + 1 < U) next_tile = phantom ? (int64_t)-1 : utile0 + i + 1;
+                    else if (i + 1 == U + LA && u + 2 < UN) next_tile = unit_tile0(u + 2);
+
+                    // ---- input-gradient chain ----
+                    const uint64_t dsp2 = pk2f(dspre, dspre);
+                    for (int s = 1; s < ns; ++s) {
+                        const BwdStep& B = p.steps[s];
+                        if (s == (ns > 3 ? 3 : 1) && next_tile != -2) { prepare_tile(next_tile, pe); pe_ready = true; }
+                        CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                        if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | (nl + s - 1));
+                        const long long tr_b0 = CNB_TR_NOW();
+                        umma::tc_fence_after();
+                        wait_buf_free();
+                        const uint32_t* ml = mset + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
+                        const float* wsig_s = smem_fptr(sWsig, order_token());
+                        if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
+                        else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
+                        else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
+                        publish(s + 1 < ns);
+                        if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | (nl + s - 1));
+                        tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
+                    }
+                }
             }
         }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
@@ -992,7 +1058,7 @@ size_t carve_bwd(const cnb_net_config* c, const Plan& pl, int n_codes, int64_t s
     w.fw.folded = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
     w.colsum = (float*)take(sizeof(float) * (size_t)n_codes * nl * kW);
     w.dz = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
-    w.masks = (uint32_t*)take(sizeof(uint32_t) * (size_t)grid * 2 * nl * 8 * kTileRows);
+    w.masks = (uint32_t*)take(sizeof(uint32_t) * (size_t)grid * 2 * 2 * nl * 8 * kTileRows);   // [grid][2 groups][2 tile parities]
     w.dspre = (float*)take(sizeof(float) * (size_t)sub_rows);
     if (fused) {
         w.spill_sig = (float*)take(sizeof(float) * (size_t)sub_rows);
@@ -1079,6 +1145,7 @@ int pipeline_end(Pipeline& pp, cudaStream_t st) {
 // K2 (+ K3 and head gradients when d_params != null) over launch-relative rows [0, S).
 struct FuseArgs {     // compositing (+ loss) fused into K2: per-ray arrays are indexed by global ray
     int kind;         // 1: seeds from d_rgb / d_depth, 2: L2 loss against target
+    int unit_tiles;   // tiles per unit of whole rays: N / gcd(N, 128)
     int white_bg; int64_t n_rays_total;
     const float *d_rgb, *d_depth, *target; float loss_scale;
     float *rgb, *depth, *acc, *sq_err;
@@ -1129,7 +1196,9 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     if (!d_params)
         for (int l = 0; l < nl; ++l) if (pl.fwd[l].folded >= 0) bp.colsum_layers |= 1u << l;
     bp.b_rgb2 = P[L.i_rgb2 + 1];
+    bp.unit_tiles = 1; bp.lookahead = 0;
     if (fuse) {
+        bp.unit_tiles = fuse->unit_tiles; bp.lookahead = fuse->unit_tiles > 1 ? 1 : 0;
         bp.fuse_comp = fuse->kind; bp.white_bg = fuse->white_bg; bp.n_rays_total = fuse->n_rays_total;
         bp.d_rgb_rays = fuse->d_rgb; bp.d_depth_rays = fuse->d_depth; bp.target = fuse->target; bp.loss_scale = fuse->loss_scale;
         bp.out_rgb = fuse->rgb; bp.out_depth = fuse->depth; bp.out_acc = fuse->acc; bp.sq_err = fuse->sq_err;
@@ -1142,7 +1211,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
 
     const int sms = num_sms();
     const int64_t tiles = (S + kTileRows - 1) / kTileRows;
-    const int64_t units = (tiles + 1) / 2;
+    const int64_t units = ((tiles + bp.unit_tiles - 1) / bp.unit_tiles + 1) / 2;      // pairs of units: one CTA runs two at a time
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
     // pipelined: leave SMs to the K3 of the previous sub-batch (the first K2 has the GPU to itself)
     if (piped && sub_index > 0 && grid > sms - pp->k3_sms && sms > pp->k3_sms) grid = sms - pp->k3_sms;
@@ -1287,13 +1356,33 @@ int finish_bwd(const cnb_net_config* c, const float* const* P, const Plan& pl, B
 // ===========================================================================
 namespace sm100 {
 
+// Units of whole rays in whole tiles: N / gcd(N, 128) tiles hold 128 / gcd(N, 128) rays.
+struct UnitShape { int tiles, rays; };
+static UnitShape unit_shape(int N) {
+    int a = N, b = kTileRows;
+    while (b) { const int t = a % b; a = b; b = t; }
+    return UnitShape{N / a, kTileRows / a};
+}
+constexpr int kMaxUnitTiles = 32;      // longer units (odd N) take the unfused path
+static bool can_fuse_compositing(int N) { return N >= 1 && N <= kTileRows && unit_shape(N).tiles <= kMaxUnitTiles; }
+// Rays per sub-batch: at most kMaxSubTiles tiles, whole units (so sub-batches start on tile boundaries and a tile
+// never straddles rays of two sub-batches or, with rows_per_code % 128 == 0, two codes).
+static int64_t sub_batch_rays(int N, int64_t n_rays) {
+    const int64_t max_rows = kMaxSubTiles * kTileRows;
+    if (n_rays * N <= max_rows) return n_rays < 1 ? 1 : n_rays;
+    const int64_t align = unit_shape(N).rays;
+    int64_t sub = max_rows / N;
+    sub -= sub % align;
+    return sub < align ? align : sub;
+}
+
 size_t bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int64_t n_rays, int N, int n_codes, int fused) {
     Plan pl;
     if (make_plan(cfg, nullptr, &pl) != CNB_OK) return 256;
     int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
-    int64_t sub_rays = fused ? (sub_rows / N < 1 ? 1 : sub_rows / N) : 0;
-    if (fused) { if (sub_rays > n_rays) sub_rays = n_rays; sub_rows = sub_rays * N; }
-    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, 148 * 2, nullptr, nullptr, (pipeline_wanted() && S > sub_rows) ? 2 : 1) + 1024;
+    int64_t sub_rays = 0;
+    if (fused) { sub_rays = sub_batch_rays(N, n_rays); sub_rows = sub_rays * N; }
+    return carve_bwd(cfg, pl, n_codes, sub_rows, sub_rays, fused, 1, num_sms(), nullptr, nullptr, (pipeline_wanted() && S > sub_rows) ? 2 : 1) + 1024;
 }
 
 // Fused render backward (mode 1: seeds given; mode 2: L2 loss against target).
@@ -1308,28 +1397,20 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
     const int64_t S = rays->n_rays * N;
     const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * N;
     if (rays->n_codes > 1 && (rows_per_code % kTileRows) != 0) return CNB_E_UNSUPPORTED;
-    int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
-    int64_t sub_rays = sub_rows / N < 1 ? 1 : sub_rows / N;
-    if (sub_rays > rays->n_rays) sub_rays = rays->n_rays;
-    if (rays->n_codes > 1) {   // sub-batches must start on tile-aligned rows so a tile never straddles codes
-        const int64_t align = kTileRows / (N % kTileRows == 0 ? kTileRows : 1);
-        (void)align;
-        while (sub_rays > 1 && (sub_rays * N) % kTileRows != 0) --sub_rays;
-        if ((sub_rays * N) % kTileRows != 0 && sub_rays < rays->n_rays) return CNB_E_UNSUPPORTED;
-    }
-    if ((kTileRows % N) == 0 && sub_rays < rays->n_rays) sub_rays -= sub_rays % (kTileRows / N);
-    sub_rows = sub_rays * N;
+    const int64_t sub_rays = sub_batch_rays(N, rays->n_rays);
+    const int64_t sub_rows = sub_rays * N;
     BwdWorkspace w;
     const int64_t n_sub = (rays->n_rays + sub_rays - 1) / sub_rays;
     int nbuf = (pipeline_wanted() && n_sub > 1) ? 2 : 1;
-    size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr, nbuf);
+    const int sms = num_sms();
+    size_t need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, sms, nullptr, nullptr, nbuf);
     if (nbuf > 1 && ws && ws_bytes < need) {     // a caller-sized workspace without the second hand-over copy: no overlap
         nbuf = 1;
-        need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, nullptr, nullptr, nbuf);
+        need = carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, sms, nullptr, nullptr, nbuf);
     }
     if (!ws || ws_bytes < need) return CNB_E_WORKSPACE;
     if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
-    carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, 148 * 2, (char*)ws, &w, nbuf);
+    carve_bwd(cfg, pl, rays->n_codes, sub_rows, sub_rays, 1, 1, sms, (char*)ws, &w, nbuf);
     Pipeline pipe;
     CNB_TRY(pipeline_begin(pipe, n_sub, d_params != nullptr));
     CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w.fw, st));
@@ -1337,15 +1418,15 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
     if (mode == 2 && sq_err)
         CNB_CUDA_TRY(cudaMemsetAsync(sq_err, 0, sizeof(float) * (size_t)(rays->n_rays / rays->rays_per_segment), st));
     CnbRaySource rs = cnb_make_ray_source(rays);
-    const bool fuse = (kTileRows % N) == 0 && (sub_rays * N) % kTileRows == 0;
+    const bool fuse = can_fuse_compositing(N);
     int sub = 0;
     for (int64_t r0 = 0; r0 < rays->n_rays; r0 += sub_rays, ++sub) {
         const int64_t nr = rays->n_rays - r0 < sub_rays ? rays->n_rays - r0 : sub_rays;
         const bool last_sub = r0 + sub_rays >= rays->n_rays;
         if (fuse) {
-            // every 128-row tile holds whole rays: compositing, the loss seed and its backward run inside K2
+            // compositing, the loss seed and its backward run inside K2 (rays may straddle the tiles of a unit)
             FuseArgs fa = {};
-            fa.kind = mode; fa.white_bg = rays->white_bg; fa.n_rays_total = rays->n_rays;
+            fa.kind = mode; fa.unit_tiles = unit_shape(N).tiles; fa.white_bg = rays->white_bg; fa.n_rays_total = rays->n_rays;
             fa.d_rgb = d_rgb; fa.d_depth = d_depth; fa.target = target; fa.loss_scale = loss_scale;
             fa.rgb = rgb; fa.depth = depth; fa.acc = acc; fa.sq_err = mode == 2 ? sq_err : nullptr;
             CNB_TRY(run_mlp_bwd(cfg, P, packed, pl, w, 0, &rs, nullptr, nullptr, nr * N, r0 * N, rays->n_codes,
@@ -1397,14 +1478,14 @@ int cnb_sm100_mlp_backward(const cnb_net_config* cfg, const float* const* P, con
     BwdWorkspace w;
     const int64_t n_sub = sub_rows > 0 ? (S + sub_rows - 1) / sub_rows : 1;
     int nbuf = (pipeline_wanted() && n_sub > 1) ? 2 : 1;
-    size_t need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr, nbuf);
+    size_t need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, num_sms(), nullptr, nullptr, nbuf);
     if (nbuf > 1 && ws && ws_bytes < need) {
         nbuf = 1;
-        need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, nullptr, nullptr, nbuf);
+        need = carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, num_sms(), nullptr, nullptr, nbuf);
     }
     if (!ws || ws_bytes < need) return CNB_E_WORKSPACE;
     if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
-    carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, 148 * 2, (char*)ws, &w, nbuf);
+    carve_bwd(cfg, pl, n_codes, sub_rows, 0, 0, 1, num_sms(), (char*)ws, &w, nbuf);
     Pipeline pipe;
     CNB_TRY(pipeline_begin(pipe, n_sub, d_params != nullptr));
     CNB_TRY(latent_and_fold(cfg, P, shape_codes, tex_codes, n_codes, w.fw, st));

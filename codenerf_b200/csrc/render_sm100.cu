@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 const int need = (g == 1) ? r + 1 : r;
                 const long long t0 = clock64();
                 while (final_count[g ^ 1] < need) {
-                    if (clock64() - t0 > 2000000000LL) { atomicExch(&umma::g_umma_timeout, 2u); break; }
+                    if (clock64() - t0 > umma::kWatchdogCycles) umma::mbar_watchdog_trip(2u);
                 }
                 __threadfence_block();
             }

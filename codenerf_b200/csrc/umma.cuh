@@ -41,17 +41,24 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug must not hang the GPU box.  On timeout the flag is set and the
-// caller's pipeline runs to completion with garbage; the host reports the failure.
+// Bounded spin: a protocol bug must not hang the GPU box, and must not be silent either.  A wait that lasts longer
+// than the watchdog (~4 s of SM clocks, three orders of magnitude above the longest legitimate wait, so time-slicing
+// or a sanitizer does not trip it) records a code and TRAPS: the launch fails, every later CUDA call on the context
+// returns an error, and the host wrappers (which check the status of every call) raise.  The flag is per translation
+// unit (it only serves post-mortem inspection under cuda-gdb); cnb_debug_pipeline_timeouts reports it, or the
+// context error, to tests.
 static __device__ unsigned int g_umma_timeout = 0;
+constexpr long long kWatchdogCycles = 8000000000LL;
+static __device__ __noinline__ void mbar_watchdog_trip(unsigned int code) {
+    atomicExch(&g_umma_timeout, code);
+    __threadfence_system();
+    __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 2000000000LL) {   // ~1 s
-            atomicExch(&g_umma_timeout, 1u);
-            return;
-        }
+        if (clock64() - t0 > kWatchdogCycles) mbar_watchdog_trip(1u);
     }
 }
 
@@ -186,7 +193,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
     if (mbar_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > 2000000000LL) { atomicExch(&g_umma_timeout, 3u); return; }
+        if (clock64() - t0 > kWatchdogCycles) mbar_watchdog_trip(3u);
     }
 }
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_out, uint32_t cols) {

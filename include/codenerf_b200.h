@@ -3,9 +3,15 @@
  *
  * One shared library (codenerf_b200/libcodenerf_b200.so), plain pointers and
  * sizes, no torch / C++ types.  Every entry point is asynchronous on the given
- * CUDA stream, never allocates or frees caller-visible memory, keeps no global
- * mutable state, and returns an int status: 0 = ok, < 0 = cnb_status below,
- * > 0 = a cudaError_t.  No exceptions or aborts cross this boundary.
+ * CUDA stream, never allocates or frees caller-visible memory, and returns an
+ * int status: 0 = ok, < 0 = cnb_status below, > 0 = a cudaError_t.  No
+ * exceptions or aborts cross this boundary.  Process-global state is limited to
+ * what this header names: the launch counter (cnb_launch_count), the optional
+ * kernel-timing record (cnb_profile_*), per-device helper streams/events, and
+ * experiment switches read from CNB_* environment variables at launch time
+ * (listed in INTEGRATION.md; none is needed for correct results).  Compute
+ * entry points may be called from several host threads as long as each call
+ * gets its own workspace.
  *
  * The reference (yuliangguo/code-nerf) has no FFI: its boundary for this path
  * is four Python callables and one nn.Module.  Each entry point cites the
@@ -176,8 +182,10 @@ int cnb_render_train_step(const cnb_net_config* cfg, const float* const* params,
 int cnb_profile_enable(int on);
 int cnb_profile_read(int kernel_id, float* ms, int cap);
 
-/* Debug aid: synchronises the device and returns non-zero if a pipeline wait inside the
- * tensor-core kernels ever hit its watchdog (a protocol bug; results are then invalid). */
+/* A pipeline wait inside the tensor-core kernels that exceeds its watchdog (a protocol bug)
+ * TRAPS: the launch fails and every later call on the context returns a cudaError_t status.
+ * This debug aid synchronises the device and returns non-zero if that happened (or if the
+ * context is in an error state for any other reason). */
 int cnb_debug_pipeline_timeouts(void);
 
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
