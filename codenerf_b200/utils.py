@@ -28,6 +28,15 @@ def _focal_args(focal):
     return float(focal), False
 
 
+def collated_focal(focal):
+    """What the reference's loops hand to get_rays: `data.SRN.__getitem__` returns a python float (src/data.py:34) and
+    DataLoader collation turns it into an fp64 tensor of shape [1], so the pixel offsets are divided in fp64
+    (`_focal_args`).  The loop mirrors (Trainer, CodeFitter) pass every python-float focal through this."""
+    if isinstance(focal, torch.Tensor):
+        return focal
+    return torch.tensor([float(focal)], dtype=torch.float64)
+
+
 def get_rays(H, W, focal, c2w):
     """Reference src/utils.py:10-19 -> (rays_o [H*W,3], viewdirs [H*W,3]), bit-exact with the
     reference's CPU result.  c2w: [4,4] (or [...,4,4] with one matrix)."""

@@ -67,3 +67,42 @@ def test_two_rank_gradient_allreduce_equals_single_process():
         ref += _object_grad(flat, obj)
     np.testing.assert_allclose(out["grad"], ref, rtol=1e-5, atol=1e-9)
     assert out["max"] == 2.0
+
+
+def _worker_tables(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank holds the full table; only the rows it owns are current (stale rows hold garbage)
+    owner = torch.tensor([0, 1, 1, 0, 1])
+    table = torch.full((5, 3), -99.0)
+    for i in range(5):
+        if int(owner[i]) == rank:
+            table[i] = float(10 * i + rank)
+    full = parallel.gather_owned_rows(table, owner)
+    b, e = parallel.shard_range(7, world, rank)
+    local = torch.arange(b, e, dtype=torch.float32).reshape(-1, 1) * torch.ones(1, 2)
+    cat = parallel.gather_varlen(local)
+    g = torch.ones(4) * (rank + 1)
+    work = parallel.allreduce_mlp_grad(g, async_op=True)
+    work.wait()
+    if rank == 0:
+        out["full"] = full.numpy().copy()
+        out["cat"] = cat.numpy().copy()
+        out["g"] = g.numpy().copy()
+    dist.destroy_process_group()
+
+
+def test_owned_rows_and_varlen_gather_two_ranks():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mgr = mp.get_context("spawn").Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_tables, args=(2, port, out), nprocs=2, join=True)
+    np.testing.assert_array_equal(out["full"][:, 0], [0, 11, 21, 30, 41])
+    np.testing.assert_array_equal(out["cat"][:, 0], np.arange(7))
+    np.testing.assert_array_equal(out["g"], [3, 3, 3, 3])
+    # without a process group everything is the identity
+    t = torch.arange(6.0).reshape(3, 2)
+    assert torch.equal(parallel.gather_owned_rows(t, [0, 0, 0]), t) and torch.equal(parallel.gather_varlen(t), t)
+    assert parallel.world() == (0, 1) and parallel.allreduce_mlp_grad(t, async_op=True).wait()

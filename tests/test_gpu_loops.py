@@ -118,3 +118,240 @@ def test_trainer_step_matches_fp32_loop():
     for a, b in zip(losses["fp32"], losses["bf16"]):
         assert abs(a - b) < 2e-3 * max(1.0, abs(a))
     assert losses["fp32"][-1] < losses["fp32"][0]
+
+
+# ---------------------------------------------------------------------------------------------
+# Batched trainer against the reference loop (src/trainer.py:54-96) restated on the CPU oracle
+def _oracle_trainer(flat0, codes_s0, codes_t0, H, W, B, focal, imgs, poses, batches, seed):
+    """`batches`: list of object-index lists, one optimiser step each.  AdamW from torch on CPU tensors over the flat
+    parameter vector (lr 1e-4) and both code tables (lr 1e-3), gradients summed over the objects of a step."""
+    P = torch.from_numpy(flat0.copy()).requires_grad_()
+    S = torch.from_numpy(codes_s0.copy()).requires_grad_()
+    T = torch.from_numpy(codes_t0.copy()).requires_grad_()
+    opt = torch.optim.AdamW([{"params": [P], "lr": 1e-4}, {"params": [S], "lr": 1e-3}, {"params": [T], "lr": 1e-3}])
+    torch.manual_seed(seed)
+    losses = []
+    for objs in batches:
+        gP = np.zeros(flat0.size, np.float32)
+        gS, gT = np.zeros_like(codes_s0), np.zeros_like(codes_t0)
+        step_losses = []
+        for o in objs:
+            dist = (1.8 - 0.8) / (2 * 64)
+            z = torch.linspace(0.8 + dist, 1.8 - dist, 64)
+            z += torch.rand(64) * (1.8 - 0.8) / (2 * 64)
+            z = z.numpy()
+            flat = P.detach().numpy()
+            s, t = S.detach().numpy()[o:o + 1], T.detach().numpy()[o:o + 1]
+            fwd = orc.render(flat, H, W, focal, poses[o], z, s, t, True)
+            d_rgb = (2.0 * (fwd["rgb"] - imgs[o]) / (3.0 * B)).astype(np.float32)
+            dP, dsc, dtc = orc.render_backward(flat, fwd, z, s, t, d_rgb, None, True)
+            gP += dP
+            gS[o] += dsc[0] + 1e-4 * s[0] / np.linalg.norm(s[0])
+            gT[o] += dtc[0] + 1e-4 * t[0] / np.linalg.norm(t[0])
+            step_losses.append(((fwd["rgb"] - imgs[o]) ** 2).reshape(-1, B * 3).mean(1).mean())
+        P.grad, S.grad, T.grad = torch.from_numpy(gP), torch.from_numpy(gS), torch.from_numpy(gT)
+        opt.step()
+        losses.append(step_losses)
+    return P.detach().numpy(), S.detach().numpy(), T.detach().numpy(), losses
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_trainer_batches_match_reference_loop_on_oracle(prec):
+    """8 optimiser steps -- batches of 3 objects, then the reference's one-object iterations -- through
+    Trainer.train_batch against the oracle-restated loop: per-object losses and the trained code rows."""
+    from codenerf_b200.trainer import Trainer
+    H = W = 32
+    B = 512
+    n_obj = 4
+    focal = 131.25 * W / 128
+    poses = np.stack([syn.look_at_pose(400 + i, 1.3) for i in range(n_obj)])
+    imgs = np.stack([syn.make_targets(500 + i, H * W) for i in range(n_obj)])
+    flat, views = syn.make_params(0)
+    batches = [[0, 1, 2], [3, 0, 1], [2, 3, 0], [1], [2], [3], [0, 2], [1, 3]]
+    torch.manual_seed(3)
+    tr = Trainer(HP, n_objects=n_obj, batch_size=B, precision=prec)
+    tr.model.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in views.items()})
+    s0 = tr.shape_codes.weight.detach().cpu().numpy().copy()
+    t0 = tr.texture_codes.weight.detach().cpu().numpy().copy()
+    P_o, S_o, T_o, L_o = _oracle_trainer(flat, s0, t0, H, W, B, focal, imgs, poses, batches, seed=4)
+    torch.manual_seed(4)
+    L_g = []
+    for objs in batches:
+        loss = tr.train_batch(focal, H, W, torch.from_numpy(imgs[objs]), torch.from_numpy(poses[objs]), objs)
+        L_g.append(loss.cpu().numpy())
+    S_g, T_g = tr.shape_codes.weight.detach().cpu().numpy(), tr.texture_codes.weight.detach().cpu().numpy()
+    P_g = np.concatenate([p.detach().cpu().numpy().ravel() for p in tr.model.parameters()])
+    worst = max(float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(b).max(), 1e-9)) for a, b in zip(L_g, L_o))
+    moved = float(np.abs(S_o - s0).mean())
+    print(f"{prec}: worst rel loss diff {worst:.2e}; mean |d code| vs oracle {np.abs(S_g - S_o).mean():.2e} (codes moved {moved:.2e}); "
+          f"mean |d param| {np.abs(P_g - P_o).mean():.2e} (moved {np.abs(P_o - flat).mean():.2e})")
+    assert worst < 2e-3
+    assert tr.niter == len(batches)
+    # the update direction is what AdamW preserves: compare the displacement of codes and weights
+    tol = 0.02 if prec == "fp32" else 0.15
+    for got, ref, start in ((S_g, S_o, s0), (T_g, T_o, t0), (P_g, P_o, flat)):
+        d_ref, d_got = ref - start, got - start
+        assert np.abs(d_got - d_ref).mean() < tol * np.abs(d_ref).mean(), (np.abs(d_got - d_ref).mean(), np.abs(d_ref).mean())
+        assert U.cosine(d_got, d_ref) > (0.999 if prec == "fp32" else 0.98)
+
+
+@pytest.mark.gpu
+def test_trainer_epoch_hooks_schedule_and_checkpoints(tmp_path):
+    """training(): crop -> full curriculum, optimiser re-created per epoch with the scheduled lr, models.pth cadence."""
+    from tests.test_data_srn import _make_tree
+    from codenerf_b200.data import SRN
+    from codenerf_b200.trainer import Trainer
+    from codenerf_b200.checkpoint import load_models
+    _make_tree(str(tmp_path), "cars_train", 3, 50, H=128, W=128)
+    ds = SRN(cat="srn_cars", splits="cars_train", data_dir=str(tmp_path), num_instances_per_obj=1, crop_img=True)
+    hp = dict(HP)
+    hp["lr_schedule"] = [{"type": "step", "lr": 1e-4, "interval": 4}, {"type": "step", "lr": 1e-3, "interval": 4}]
+    hp["check_points"] = 3
+    torch.manual_seed(0)
+    np.random.seed(0)
+    tr = Trainer(hp, n_objects=len(ds), batch_size=2048, precision="bf16")
+    seen = []
+    orig = tr.train_batch
+
+    def spy(focal, H, W, imgs, poses, idx, z_vals=None):
+        seen.append((H, W, tr.opts.param_groups[0]["lr"], tr.opts.param_groups[1]["lr"], list(idx)))
+        return orig(focal, H, W, imgs, poses, idx, z_vals)
+
+    tr.train_batch = spy
+    logs = []
+    out = str(tmp_path / "exp")
+    tr.training(ds, iters_crop=4, iters_all=7, objects_per_step=2, save_dir=out, log=lambda it, psnr: logs.append((it, psnr)))
+    # epochs of 2 steps (3 objects, 2 per step): crop epochs until niter >= 4, then full views until 7
+    assert [s[:2] for s in seen] == [(64, 64)] * 4 + [(128, 128)] * 3
+    assert [s[4] for s in seen[:2]] == [[0, 1], [2]]
+    # lr of an epoch is fixed at its start: niter 0, 2 -> 1e-4; niter 4, 6 -> 5e-5 (trainer.py:52, :122-128)
+    assert [s[2] for s in seen] == [1e-4, 1e-4, 1e-4, 1e-4, 5e-5, 5e-5, 5e-5]
+    assert [s[3] for s in seen] == [1e-3] * 4 + [5e-4] * 3
+    assert tr.niter == 7 and tr.nepoch == 4 and len(logs) == 7 and all(np.isfinite(p) for _, p in logs)
+    import os
+    assert sorted(os.listdir(out)) == ["0.pth", "3.pth", "6.pth", "models.pth"]
+    saved, ms, mt = load_models(os.path.join(out, "models.pth"))
+    assert saved["niter"] == 7 and saved["shape_code_params"]["weight"].shape == (3, 256)
+
+
+# ---------------------------------------------------------------------------------------------
+# Multi-object fit / eval drivers against the one-object loops
+@pytest.mark.gpu
+def test_fit_batch_equals_per_object_fit():
+    from codenerf_b200.optimizer import CodeFitter
+    H = W = 16
+    B = H * W // 2
+    focal = 131.25 * W / 128
+    n_obj, n_views, steps = 3, 2, 12
+    flat, _ = syn.make_params(0)
+    poses = np.stack([[syn.look_at_pose(300 + 7 * o + i, 1.3) for i in range(n_views)] for o in range(n_obj)])
+    imgs = np.stack([_targets_from_hidden_code(flat, H, W, focal, poses[o], 901 + 10 * o) for o in range(n_obj)])
+    mean_s = torch.from_numpy(syn.make_codes(77, 1)[0])
+    mean_t = torch.from_numpy(syn.make_codes(78, 1)[0])
+    model, _ = U.make_model("bf16")
+    fitter = CodeFitter(model, HP, batch_size=B, num_opts=steps)
+    torch.manual_seed(11)
+    zs = torch.stack([fitter._z() for _ in range(steps * n_views * n_obj)]).reshape(steps, n_views, n_obj, 64)
+    s_b, t_b, h_b = fitter.fit_batch(focal, H, W, torch.from_numpy(imgs), torch.from_numpy(poses), mean_s, mean_t,
+                                     lr=1e-2, lr_half_interval=5, z_vals=zs)
+    assert s_b.shape == (n_obj, 256) and h_b.shape == (steps, n_obj)
+    for o in range(n_obj):
+        # the one-object loop with the same z rows: patch the generator draw
+        it = iter(zs[:, :, o].reshape(-1, 64))
+        fitter._z = lambda: next(it)
+        s1, t1, h1 = fitter.fit(focal, H, W, torch.from_numpy(imgs[o]), torch.from_numpy(poses[o]), mean_s, mean_t,
+                                lr=1e-2, lr_half_interval=5)
+        assert abs(h1[-1] - float(h_b[-1, o])) < 0.02, (o, h1[-1], float(h_b[-1, o]))
+        assert np.abs(s1.cpu().numpy() - s_b[o:o + 1].cpu().numpy()).max() < 5e-3
+        assert np.abs(t1.cpu().numpy() - t_b[o:o + 1].cpu().numpy()).max() < 5e-3
+    del fitter._z
+
+
+@pytest.mark.gpu
+def test_latent_fit_psnr_parity_reference_config():
+    """The reference's own fitting schedule (optimize.py defaults: 200 steps, lr 1e-2 halved every 50) on 24x24 views:
+    oracle loop vs the batched bf16 fit, optimised-code PSNR within 0.05 dB (north star), and held-out-view PSNR of the
+    fitted codes against the oracle's render of the same codes."""
+    from codenerf_b200.optimizer import CodeFitter, render_dataset
+    H = W = 24
+    B = H * W // 2
+    focal = 131.25 * W / 128
+    steps = 200
+    flat, _ = syn.make_params(0)
+    poses = np.stack([syn.look_at_pose(300 + i, 1.3) for i in range(4)])
+    imgs = _targets_from_hidden_code(flat, H, W, focal, poses, 901)
+    torch.manual_seed(21)
+    model, _ = U.make_model("bf16")
+    fitter = CodeFitter(model, HP, batch_size=B, num_opts=steps)
+    zs = torch.stack([fitter._z() for _ in range(steps * 2)]).reshape(steps, 2, 1, 64)
+    mean_s = torch.from_numpy(syn.make_codes(77, 1)[0])
+    mean_t = torch.from_numpy(syn.make_codes(78, 1)[0])
+    s_b, t_b, h_b = fitter.fit_batch(focal, H, W, torch.from_numpy(imgs[None, :2]), torch.from_numpy(poses[None, :2]),
+                                     mean_s, mean_t, lr=1e-2, lr_half_interval=50, z_vals=zs)
+    # oracle loop with the same z rows
+    sc = torch.from_numpy(syn.make_codes(77, 1)).clone().requires_grad_()
+    tc = torch.from_numpy(syn.make_codes(78, 1)).clone().requires_grad_()
+    nopts = 0
+    mk = lambda: torch.optim.AdamW([{"params": sc, "lr": 1e-2 * 2 ** (-(nopts // 50))}, {"params": tc, "lr": 1e-2 * 2 ** (-(nopts // 50))}])
+    opt = mk()
+    h_o = []
+    while nopts < steps:
+        gs, gt = np.zeros((1, 256), np.float32), np.zeros((1, 256), np.float32)
+        for v in range(2):
+            z = zs[nopts, v, 0].numpy()
+            s_n, t_n = sc.detach().numpy(), tc.detach().numpy()
+            fwd = orc.render(flat, H, W, focal, poses[v], z, s_n, t_n, True)
+            d_rgb = (2.0 * (fwd["rgb"] - imgs[v]) / (3.0 * B)).astype(np.float32)
+            _, dsc, dtc = orc.render_backward(flat, fwd, z, s_n, t_n, d_rgb, None, True, want_param_grads=False)
+            gs += dsc + 1e-4 * s_n / np.linalg.norm(s_n)
+            gt += dtc + 1e-4 * t_n / np.linalg.norm(t_n)
+            mses = ((fwd["rgb"] - imgs[v]) ** 2).reshape(-1, B * 3).mean(1)
+        sc.grad, tc.grad = torch.from_numpy(gs), torch.from_numpy(gt)
+        opt.step()
+        h_o.append(-10 * math.log(mses.mean()) / math.log(10))
+        nopts += 1
+        if nopts % 50 == 0:
+            opt = mk()
+    print("200-step fit PSNR: oracle %.3f  bf16 batched %.3f  (start %.3f)" % (h_o[-1], float(h_b[-1, 0]), h_o[0]))
+    assert h_o[-1] > h_o[0] + 1.0
+    assert abs(float(h_b[-1, 0]) - h_o[-1]) < 0.05
+    # held-out views: PSNR of the codes each loop found, rendered by its own path (fixed z so both see the same rays)
+    zf = torch.from_numpy(orc.z_vals(0.8, 1.8, 64, z_fixed=True))
+    out = render_dataset(model, HP, focal, H, W, torch.from_numpy(poses[None, 2:]), s_b, t_b,
+                         targets=torch.from_numpy(imgs[None, 2:]), batch_size=B, z_vals=zf.expand(1, 2, 64))
+    for v in range(2):
+        ref = orc.render(flat, H, W, focal, poses[2 + v], zf.numpy(), sc.detach().numpy(), tc.detach().numpy(), True)["rgb"]
+        p_o = -10 * math.log(((ref - imgs[2 + v]) ** 2).reshape(-1, B * 3).mean(1).mean()) / math.log(10)
+        print("held-out view %d: oracle %.3f dB, bf16 %.3f dB" % (v, p_o, float(out["psnr"][v])))
+        assert abs(float(out["psnr"][v]) - p_o) < 0.05
+
+
+@pytest.mark.gpu
+def test_render_dataset_equals_view_by_view_render():
+    import codenerf_b200 as cn
+    from codenerf_b200.optimizer import render_dataset
+    H = W = 32
+    B = 512
+    focal = 131.25 * W / 128
+    n_obj, n_views = 3, 5
+    model, flat = U.make_model("bf16")
+    poses = torch.from_numpy(np.stack([[syn.look_at_pose(40 + 9 * o + v, 1.3) for v in range(n_views)] for o in range(n_obj)]))
+    sc, tc = torch.from_numpy(syn.make_codes(5, n_obj)).cuda(), torch.from_numpy(syn.make_codes(6, n_obj)).cuda()
+    tg = torch.from_numpy(syn.make_targets(8, n_obj * n_views * H * W).reshape(n_obj, n_views, H * W, 3))
+    torch.manual_seed(2)
+    zs = torch.stack([cn.make_z_vals(0.8, 1.8, 64) for _ in range(n_obj * n_views)]).reshape(n_obj, n_views, 64)
+    seen = []
+    out = render_dataset(model, HP, focal, H, W, poses, sc, tc, targets=tg, batch_size=B, views_per_launch=4, z_vals=zs,
+                         keep_images=True, on_batch=lambda pairs, rgb, d, a: seen.append(pairs.clone()))
+    assert out["rgb"].shape == (n_obj * n_views, H * W, 3) and torch.cat(seen).shape == (n_obj * n_views, 2)
+    f64 = torch.tensor([focal], dtype=torch.float64)
+    for o in range(n_obj):
+        for v in range(n_views):
+            with torch.no_grad():
+                rgb, _, _ = cn.render_view(model, H, W, f64, poses[o, v], zs[o, v], sc[o:o + 1], tc[o:o + 1])
+            k = o * n_views + v
+            assert tuple(out["pairs"][k].tolist()) == (o, v)
+            assert torch.equal(rgb, out["rgb"][k])                      # batching never changes a ray's colour
+            mse = ((rgb.cpu() - tg[o, v]) ** 2).reshape(-1, B * 3).mean(1).mean()
+            assert abs(float(out["psnr"][k]) - (-10 * math.log10(float(mse)))) < 1e-3
