@@ -624,3 +624,12 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+
+/* bench.py's reference arm: torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU baseline is allowed all host cores. */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}

@@ -66,6 +66,11 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the port (bench.py: torchrun pins OMP_NUM_THREADS=1; the CPU baseline may use every core)."""
+    lib().orc_set_num_threads(ctypes.c_int(int(n)))
+
+
 def param_count(cfg=None):
     c = _cfg(cfg)
     return int(lib().orc_param_count(ctypes.byref(c)))
