@@ -9,8 +9,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcodenerf_b200.so")
 # CNB_LIB=trace selects the instrumented build (`python -m codenerf_b200.build --trace`); perf-debugging scripts only
-if os.environ.get("CNB_LIB") == "trace":
-    LIB_PATH = os.path.join(_HERE, "libcodenerf_b200_trace.so")
+if os.environ.get("CNB_LIB"):       # "trace", or an experiment variant built with `build.py --variant=<name> -D...`
+    LIB_PATH = os.path.join(_HERE, "libcodenerf_b200_%s.so" % os.environ["CNB_LIB"])
 
 PRECISION_BF16 = 0
 PRECISION_FP32 = 1
@@ -53,7 +53,7 @@ EXPORTS = [
     "cnb_volume_rendering_backward", "cnb_packed_weights_bytes", "cnb_pack_weights", "cnb_mlp_workspace_bytes",
     "cnb_mlp_forward", "cnb_mlp_backward", "cnb_render_workspace_bytes", "cnb_render_forward",
     "cnb_render_backward", "cnb_render_train_step", "cnb_launch_count", "cnb_debug_pipeline_timeouts",
-    "cnb_profile_enable", "cnb_profile_read",
+    "cnb_profile_enable", "cnb_profile_read", "cnb_set_option", "cnb_clear_option", "cnb_get_option",
 ]
 
 _lib = None
@@ -117,6 +117,12 @@ def load():
     L.cnb_profile_enable.argtypes = [i32]
     L.cnb_profile_read.restype = i32
     L.cnb_profile_read.argtypes = [i32, ctypes.POINTER(ctypes.c_float), i32]
+    L.cnb_set_option.restype = i32
+    L.cnb_set_option.argtypes = [ctypes.c_char_p, i64]
+    L.cnb_clear_option.restype = i32
+    L.cnb_clear_option.argtypes = [ctypes.c_char_p]
+    L.cnb_get_option.restype = i64
+    L.cnb_get_option.argtypes = [ctypes.c_char_p, i64]
     _lib = L
     return L
 
@@ -124,6 +130,19 @@ def load():
 def check(rc):
     if rc != 0:
         raise RuntimeError(f"codenerf_b200: {load().cnb_strerror(int(rc)).decode()} (status {rc})")
+
+
+def set_option(name, value):
+    """cnb_set_option: tuning / experiment switch (see include/codenerf_b200.h)."""
+    check(load().cnb_set_option(name.encode(), int(value)))
+
+
+def clear_option(name):
+    check(load().cnb_clear_option(name.encode()))
+
+
+def get_option(name, default=0):
+    return int(load().cnb_get_option(name.encode(), int(default)))
 
 
 def precision_id(p):

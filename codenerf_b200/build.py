@@ -32,15 +32,19 @@ def needs_build(lib=LIB):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, trace=False):
+def build(force=False, verbose=False, trace=False, variant=None, defines=()):
+    """`variant` + `defines`: an experiment build libcodenerf_b200_<variant>.so compiled with the given -D flags
+    (selected at run time with CNB_LIB=<variant>; A/B measurements in one GPU session)."""
     lib = LIB_TRACE if trace else LIB
+    if variant:
+        lib = os.path.join(HERE, f"libcodenerf_b200_{variant}.so")
     if not force and not needs_build(lib):
         return lib
     objs = []
     procs = []
-    obj_dir = os.path.join(HERE, "..", "build", "trace" if trace else "")
+    obj_dir = os.path.join(HERE, "..", "build", variant if variant else ("trace" if trace else ""))
     os.makedirs(obj_dir, exist_ok=True)
-    extra = os.environ.get("CNB_NVCC_EXTRA", "").split() + (["-DCNB_TRACE"] if trace else [])
+    extra = os.environ.get("CNB_NVCC_EXTRA", "").split() + (["-DCNB_TRACE"] if trace else []) + ["-D" + d for d in defines]
     for s in SOURCES:
         o = os.path.join(obj_dir, s.replace(".cu", ".o"))
         cmd = [_nvcc()] + extra + NVCC_FLAGS + ["-Xptxas", "-v" if verbose else "-O3", "-c", os.path.join(CSRC, s), "-o", o]
@@ -60,4 +64,7 @@ def build(force=False, verbose=False, trace=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv))
+    var = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--variant=")]
+    defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trace="--trace" in sys.argv,
+                variant=var[0] if var else None, defines=defs))

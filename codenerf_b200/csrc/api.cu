@@ -3,6 +3,10 @@
 #include "common.cuh"
 #include "mlp_fp32.cuh"
 #include "render_sm100.cuh"
+#include <cctype>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
 
 std::atomic<long long> g_cnb_launches{0};
 
@@ -23,6 +27,52 @@ extern "C" const char* cnb_strerror(int status) {
     if (status > 0) return cudaGetErrorString((cudaError_t)status);
     return "codenerf_b200: unknown status";
 }
+
+// ---- options --------------------------------------------------------------------------------
+namespace {
+struct Opt { const char* name; bool set; int64_t value; };
+Opt g_opts[] = {
+    {"sub_tiles", false, 0},      // 128-row tiles per backward sub-batch (training stash: ~1 MB per tile); default 8192
+    {"bwd_pairs", false, 0},      // K2 on CTA pairs (cta_group::2)
+    {"cta_pairs", false, 0},      // K1 on CTA pairs
+    {"weight_mcast", false, 0},   // 2 | 4: CTAs per cluster sharing one multicast weight stream
+    {"epi_warps", false, 0},      // 8: eight epilogue warps per accumulator in K1
+    {"fwd_kernel_ts", false, 0},  // 1: tensor-memory-operand forward kernel
+    {"k3_overlap", false, 0},     // 1: K3 of sub-batch i on a second stream under K2 of sub-batch i + 1
+    {"k3_sms", false, 0},         // SMs left to K3 when overlapped
+    {"k3_items_per_sm_x10", false, 0},
+};
+std::mutex g_opt_mu;
+}  // namespace
+
+int64_t cnb_option(const char* name, int64_t dflt) {
+    {
+        std::lock_guard<std::mutex> lk(g_opt_mu);
+        for (Opt& o : g_opts) if (!strcmp(o.name, name) && o.set) return o.value;
+    }
+    char env[64] = "CNB_";
+    size_t n = 4;
+    for (const char* c = name; *c && n + 1 < sizeof(env); ++c) env[n++] = (char)toupper((unsigned char)*c);
+    env[n] = 0;
+    const char* e = getenv(env);
+    return e && *e ? (int64_t)atoll(e) : dflt;
+}
+
+extern "C" int cnb_set_option(const char* name, int64_t value) {
+    if (!name) return CNB_E_INVALID;
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    for (Opt& o : g_opts) if (!strcmp(o.name, name)) { o.set = true; o.value = value; return CNB_OK; }
+    return CNB_E_INVALID;
+}
+
+extern "C" int cnb_clear_option(const char* name) {
+    if (!name) return CNB_E_INVALID;
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    for (Opt& o : g_opts) if (!strcmp(o.name, name)) { o.set = false; return CNB_OK; }
+    return CNB_E_INVALID;
+}
+
+extern "C" int64_t cnb_get_option(const char* name, int64_t dflt) { return name ? cnb_option(name, dflt) : dflt; }
 
 // ---- kernel timing aid --------------------------------------------------------------------
 namespace {

@@ -19,6 +19,18 @@
 
 using namespace sm100;
 
+// Where K2 reads the rows every thread needs at the same address (see sm100_common.cuh, ConstRows): 1 = constant
+// memory (uniform loads), 0 = shared memory (LDS broadcasts; the launch-wide rows are then staged like the folded ones).
+// Measured (round 2, A/B in one session): constant memory is SLOWER for K2 -- 9.55 ms all shared, 9.9 heads constant,
+// 10.0 biases constant, 10.5 both: the uniform loads (LDCU.128) are served at a lower rate than LDS broadcasts.
+#ifndef CNB_K2_BIAS_CONST
+#define CNB_K2_BIAS_CONST 0
+#endif
+#ifndef CNB_K2_HEADS_CONST
+#define CNB_K2_HEADS_CONST 0
+#endif
+constexpr int kHeadSrc = CNB_K2_HEADS_CONST ? 2 : 1;
+
 #ifdef CNB_TRACE
 extern "C" int cnb_debug_events_bwd(unsigned long long* out, unsigned int* counts, int reset) {
     if (out && cudaMemcpyFromSymbol(out, sm100::g_events, sizeof(unsigned long long) * 4 * 16384) != cudaSuccess) return -1;
@@ -202,8 +214,8 @@ __device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const u
 #pragma unroll
         for (int i = 0; i < 4; ++i) v[i] = pk2(rr[j8 * 8 + 2 * i], rr[j8 * 8 + 2 * i + 1]);
         if (ADD_SIGMA) {
-            const float4 w0 = ld_vec4<true>(w_sigma + col);      // shared-memory copy of the sigma-head weights
-            const float4 w1 = ld_vec4<true>(w_sigma + col + 4);
+            const float4 w0 = ld_vec4<kHeadSrc>(w_sigma + col);  // sigma-head weights: constant memory (crow_ptr) or shared
+            const float4 w1 = ld_vec4<kHeadSrc>(w_sigma + col + 4);
             v[0] = ffma2(dsp2, pk2f(w0.x, w0.y), v[0]); v[1] = ffma2(dsp2, pk2f(w0.z, w0.w), v[1]);
             v[2] = ffma2(dsp2, pk2f(w1.x, w1.y), v[2]); v[3] = ffma2(dsp2, pk2f(w1.z, w1.w), v[3]);
         }
@@ -272,9 +284,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     uint64_t* buf_free = aux_ready + 2;          // [2] aux warp finished reading the operand buffer
     uint32_t* tmem_slot = (uint32_t*)(buf_free + 2);
     float4* sRing = (float4*)(tmem_slot + 4);      // [2 groups][256] per-sample (sigma, r, g, b), then seeds: two tiles per group
-    float* sBias = (float*)(sRing + 4 * kTileRows);  // [2 groups][2 buffers][256] bias row of the layer being drained
-    float* sWsig = sBias + 4 * kW;                  // [256] sigma-head weights
-    float* sWrgb = sWsig + kW;                      // [3][128] rgb.2 weights
+    float* sBias = (float*)(sRing + 4 * kTileRows);  // [2 groups][2 buffers][256] per-code (folded) bias row of the layer being drained
+    float* sWsig = sBias + 4 * kW;                  // (CNB_K2_HEADS_CONST == 0) [256] sigma-head weights, [3][128] rgb.2 weights
+    float* sWrgb = sWsig + kW;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nl = p.n_layers, ns = p.n_steps;
@@ -298,8 +310,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         umma::fence_mbar_init();
     }
     if (warp == 1) { if (CG == 2) umma::tmem_alloc2(tmem_slot, 512); else umma::tmem_alloc(tmem_slot, 512); }
-    for (int i = threadIdx.x; i < kW; i += kBwdThreads) sWsig[i] = __ldg(p.w_sigma + i);
-    for (int i = threadIdx.x; i < 3 * (kW / 2); i += kBwdThreads) sWrgb[i] = __ldg(p.w_rgb2 + i);
+    if (!CNB_K2_HEADS_CONST) {
+        for (int i = threadIdx.x; i < kW; i += kBwdThreads) sWsig[i] = __ldg(p.w_sigma + i);
+        for (int i = threadIdx.x; i < 3 * (kW / 2); i += kBwdThreads) sWrgb[i] = __ldg(p.w_rgb2 + i);
+    }
     umma::tc_fence_before();
     if (kCluster > 1) umma::cluster_sync_all(); else __syncthreads();
     umma::tc_fence_after();
@@ -540,9 +554,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     HeadAcc hacc = {0ull, 0ull, 0ull, 0ull, pol_keep};
                     for (int l = 0; l < nl; ++l) {
                         const FwdLayer& L = p.layers[l];
+                        // code-conditioned layers: the tile's folded bias row is staged in shared memory (2 floats per thread,
+                        // in flight during the wait); every other layer reads its row from constant memory
+                        const bool staged = L.folded >= 0 || !CNB_K2_BIAS_CONST;
                         const float* bias_g = L.folded >= 0 ? p.folded + ((size_t)code * p.n_folded + L.folded) * kW : L.bias;
                         float2 bias2 = make_float2(0.f, 0.f);
-                        if (2 * tg < L.n_halves * 128) bias2 = __ldg(reinterpret_cast<const float2*>(bias_g) + tg);   // in flight during the wait
+                        if (staged && 2 * tg < L.n_halves * 128) bias2 = __ldg(reinterpret_cast<const float2*>(bias_g) + tg);
                         CNB_TR(tr_wacc_f, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | l);      // accumulator visible: epilogue starts
                         const long long tr_p0 = CNB_TR_NOW();
@@ -550,22 +567,40 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         const bool last = (l + 1 == nl);
                         const bool store = !last || p.stash;
                         if (store) wait_buf_free();
-                        // the layer's bias row goes through shared memory: 2 floats per thread, then LDS broadcasts
-                        float* sb = sB + bsel * kW; bsel ^= 1u;
-                        if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
-                        const uint32_t tok = bar_sync_token(1 + g, 128);
-                        const float* bias = smem_fptr(sb, tok);
-                        const float* wsig_s = smem_fptr(sWsig, tok);     // per-layer token: the staged rows are read inside this layer
-                        const float* wrgb_s = smem_fptr(sWrgb, tok);     // (an invariant address would be hoisted out of the tile loop)
                         uint32_t* ml = mset + (size_t)l * 8 * kTileRows;
-                        if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                        else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                        else if (p.fuse_comp) {
-                            if (store) fwd_epilogue_layer<4, 2, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                            else fwd_epilogue_layer<4, 2, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
+                        // head weights: constant memory, or the shared-memory copy (a per-layer token keeps the loads inside the layer)
+                        const uint32_t htok = CNB_K2_HEADS_CONST ? 0u : order_token();
+                        const float* wsig_c = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWsig) : smem_fptr(sWsig, htok);
+                        const float* wrgb_c = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWrgb) : smem_fptr(sWrgb, htok);
+                        if (staged) {
+                            float* sb = sB + bsel * kW; bsel ^= 1u;
+                            if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
+                            const uint32_t tok = bar_sync_token(1 + g, 128);
+                            const float* bias = smem_fptr(sb, tok);
+                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            else if (p.fuse_comp) {
+                                if (store) fwd_epilogue_layer<4, 2, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                else fwd_epilogue_layer<4, 2, false, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            }
+                            else if (store) fwd_epilogue_layer<4, 0, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            else fwd_epilogue_layer<4, 0, false, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                        } else {
+                            // fixed constant-memory slots (crow_slot): immediate addresses, uniform loads
+                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 1 * kW), a8, wsig_c, wrgb_c, hacc, ml);
+                            else if (L.n_halves == 2) {
+                                if (l == 0) fwd_epilogue_layer<8, 0, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 0 * kW), a8, wsig_c, wrgb_c, hacc, ml);
+                                else fwd_epilogue_layer<8, 0, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 2 * kW), a8, wsig_c, wrgb_c, hacc, ml);
+                            } else {
+                                const float* bias = crow_ptr(kCrowBias + 3 * kW);
+                                if (p.fuse_comp) {
+                                    if (store) fwd_epilogue_layer<4, 2, true, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                    else fwd_epilogue_layer<4, 2, false, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                }
+                                else if (store) fwd_epilogue_layer<4, 0, true, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                else fwd_epilogue_layer<4, 0, false, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            }
                         }
-                        else if (store) fwd_epilogue_layer<4, 0, true, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
-                        else fwd_epilogue_layer<4, 0, false, true, true>(taddr, bias, a8, wsig_s, wrgb_s, hacc, ml);
                         if (store) publish(!last);
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | l);      // epilogue done, operand published
                         tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
@@ -580,14 +615,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     }
                     float sig_pre;
                     { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
-                    const float x = sig_pre + __ldg(p.b_sigma);
+                    const float x = sig_pre + crow(kCrowBsig);
                     if (i & 1) x_odd = x; else x_even = x;
                     if (p.fuse_comp) {
                         // per-ray compositing, loss seed and compositing backward of every ray that ends in this tile
                         float a0, a1, cr, cg, cb;
-                        unpk2(hacc.r2, a0, a1); cr = a0 + a1 + __ldg(p.b_rgb2 + 0);
-                        unpk2(hacc.g2, a0, a1); cg = a0 + a1 + __ldg(p.b_rgb2 + 1);
-                        unpk2(hacc.b2, a0, a1); cb = a0 + a1 + __ldg(p.b_rgb2 + 2);
+                        unpk2(hacc.r2, a0, a1); cr = a0 + a1 + crow(kCrowBsig + 1);
+                        unpk2(hacc.g2, a0, a1); cg = a0 + a1 + crow(kCrowBsig + 2);
+                        unpk2(hacc.b2, a0, a1); cb = a0 + a1 + crow(kCrowBsig + 3);
                         ring[((i & 1) << 7) + row] = make_float4(cnb_softplus(x), cr, cg, cb);
                         umma::named_bar_sync(1 + g, 128);
                         const int j_lo = (i * kTileRows) / N, j_hi = ((i + 1) * kTileRows) / N;      // rays of the unit ending in tile i
@@ -629,7 +664,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
                     wait_buf_free();
                     {
-                        const float* wrgb_s = smem_fptr(sWrgb, order_token());
+                        const float* wrgb_s = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWrgb) : smem_fptr(sWrgb, order_token());
                         const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
 #pragma unroll
                         for (int c8 = 0; c8 < 16; ++c8) {
@@ -638,9 +673,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             uint32_t w[4];
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
-                                const float4 w0 = ld_vec4<true>(wrgb_s + col + hh * 4);
-                                const float4 w1 = ld_vec4<true>(wrgb_s + (kW / 2) + col + hh * 4);
-                                const float4 w2 = ld_vec4<true>(wrgb_s + kW + col + hh * 4);
+                                const float4 w0 = ld_vec4<kHeadSrc>(wrgb_s + col + hh * 4);
+                                const float4 w1 = ld_vec4<kHeadSrc>(wrgb_s + (kW / 2) + col + hh * 4);
+                                const float4 w2 = ld_vec4<kHeadSrc>(wrgb_s + kW + col + hh * 4);
                                 uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
                                 uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
                                 float f0, f1, f2, f3; unpk2(v0, f0, f1); unpk2(v1, f2, f3);
@@ -673,7 +708,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         umma::tc_fence_after();
                         wait_buf_free();
                         const uint32_t* ml = mset + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
-                        const float* wsig_s = smem_fptr(sWsig, order_token());
+                        const float* wsig_s = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWsig) : smem_fptr(sWsig, order_token());
                         if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                         else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
                         else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
@@ -1014,8 +1049,11 @@ __global__ void k_l2_seed_sm100(const float* __restrict__ rgb, const float* __re
 // ===========================================================================
 // Host side
 
-// rows per sub-batch = 128 x this: 8192 tiles = 1 Mi rows (stash ~ 8 GB); CNB_SUB_TILES overrides (experiments)
-static const int64_t kMaxSubTiles = [] { const char* e = getenv("CNB_SUB_TILES"); const long v = e ? atol(e) : 0; return (int64_t)(v >= 256 ? v : 8192); }();
+// rows per sub-batch = 128 x this: 8192 tiles = 1 Mi rows (training stash ~ 8 GB).  Larger sub-batches are faster
+// (fewer split-K flushes of the weight gradient: 16.3 -> 15.65 ms per 32768-tile step at 32768) and need ~1 MB of
+// workspace per tile; the Python layer raises the option `sub_tiles` when the device has the memory.
+static int64_t max_sub_tiles() { const int64_t v = cnb_option("sub_tiles", 8192); return v >= 256 ? v : 8192; }
+#define kMaxSubTiles (max_sub_tiles())
 
 struct StashLayout {
     uint32_t a_slot[kMaxLayers + 1], dir_slot, d_slot[kMaxLayers], a_tile_bytes, d_tile_bytes;
@@ -1056,6 +1094,7 @@ size_t carve_bwd(const cnb_net_config* c, const Plan& pl, int n_codes, int64_t s
     const int nf = c->shape_blocks + c->texture_blocks, nl = pl.n_layers;
     w.fw.z = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
     w.fw.folded = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    w.fw.rows = (float*)take(sizeof(ConstRows));
     w.colsum = (float*)take(sizeof(float) * (size_t)n_codes * nl * kW);
     w.dz = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
     w.masks = (uint32_t*)take(sizeof(uint32_t) * (size_t)grid * 2 * 2 * nl * 8 * kTileRows);   // [grid][2 groups][2 tile parities]
@@ -1119,12 +1158,11 @@ PipelineResources* pipeline_resources() {
     return &r;
 }
 bool pipeline_wanted() {
-    static const int want = [] { const char* e = getenv("CNB_K3_OVERLAP"); return e ? atoi(e) : 0; }();   // measured: no gain
-    return want != 0;
+    return cnb_option("k3_overlap", 0) != 0;      // measured: no gain
 }
 int pipeline_begin(Pipeline& pp, int64_t n_sub, bool training) {
     const bool want = pipeline_wanted();
-    static const int k3_sms = [] { const char* e = getenv("CNB_K3_SMS"); return e ? atoi(e) : 40; }();
+    const int k3_sms = (int)cnb_option("k3_sms", 40);
     pp = Pipeline();
     if (!want || !training || n_sub < 2) return CNB_OK;
     PipelineResources* r = pipeline_resources();
@@ -1220,10 +1258,10 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         pp->pending[buf] = false;
     }
     const size_t smem = 1024 + 2 * (size_t)kATile + (size_t)kNumStages * kSlot + 256 + 4 * kTileRows * sizeof(float4) +
-                        sizeof(float) * (4 * kW + kW + 3 * (kW / 2));
+                        sizeof(float) * (4 * kW + (CNB_K2_HEADS_CONST ? 0 : kW + 3 * (kW / 2)));
     // CNB_WEIGHT_MCAST=2: clusters of 2 share one multicast weight stream (+2.5 % in K2 in a back-to-back run, within
     // the box-to-box noise of the bench: left opt-in)
-    const int use_pairs = [] { const char* e = getenv("CNB_BWD_PAIRS"); return e ? atoi(e) : 0; }();     // read per launch
+    const int use_pairs = (int)cnb_option("bwd_pairs", 0);
     const bool pairs = use_pairs && grid == sms;
     const int mc = pairs ? 2 : (grid == sms ? weight_multicast() : 1);      // cluster size
     if (pairs) CNB_TRY(make_weight_maps(packed, pl.total_bytes, &bp.maps));
@@ -1271,7 +1309,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         add(l, L.rgb0_w, kW, 0, kW, 4, sl.a_slot[l], 0);
     }
     // split rows into ~k3_items_per_sm work items per SM (each ends with an atomic flush of its dW tile), >= 8 half-tiles each
-    static const double k3_items_per_sm = [] { const char* e = getenv("CNB_K3_ITEMS_PER_SM"); return e ? atof(e) : 2.0; }();
+    const double k3_items_per_sm = (double)cnb_option("k3_items_per_sm_x10", 20) / 10.0;
     double total_cost = 0;
     for (int i = 0; i < np; ++i) total_cost += (double)wp.prob[i].m_blocks + (wp.prob[i].is_dir ? 0.5 : wp.prob[i].n_blocks);   // HBM bytes per half-tile
     const int64_t H = tiles * 2;
@@ -1366,14 +1404,15 @@ static UnitShape unit_shape(int N) {
 constexpr int kMaxUnitTiles = 32;      // longer units (odd N) take the unfused path
 static bool can_fuse_compositing(int N) { return N >= 1 && N <= kTileRows && unit_shape(N).tiles <= kMaxUnitTiles; }
 // Rays per sub-batch: at most kMaxSubTiles tiles, whole units (so sub-batches start on tile boundaries and a tile
-// never straddles rays of two sub-batches or, with rows_per_code % 128 == 0, two codes).
+// never straddles rays of two sub-batches or, with rows_per_code % 128 == 0, two codes).  (Rounding the size down to
+// whole waves of 2 x #SMs units was measured: the extra launch costs more than the fuller last round gains.)
 static int64_t sub_batch_rays(int N, int64_t n_rays) {
     const int64_t max_rows = kMaxSubTiles * kTileRows;
     if (n_rays * N <= max_rows) return n_rays < 1 ? 1 : n_rays;
-    const int64_t align = unit_shape(N).rays;
-    int64_t sub = max_rows / N;
-    sub -= sub % align;
-    return sub < align ? align : sub;
+    const UnitShape us = unit_shape(N);
+    int64_t units = kMaxSubTiles / us.tiles;
+    if (units < 1) units = 1;
+    return units * us.rays;
 }
 
 size_t bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int64_t n_rays, int N, int n_codes, int fused) {
@@ -1414,6 +1453,10 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
     Pipeline pipe;
     CNB_TRY(pipeline_begin(pipe, n_sub, d_params != nullptr));
     CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w.fw, st));
+#if CNB_K2_BIAS_CONST || CNB_K2_HEADS_CONST
+    ConstRowsScope crs;                    // launch-wide bias rows and head weights -> constant memory, for K2
+    CNB_TRY(crs.begin(cfg, P, pl, w.fw.rows, st));
+#endif
     CNB_CUDA_TRY(cudaMemsetAsync(w.colsum, 0, sizeof(float) * (size_t)rays->n_codes * pl.n_layers * kW, st));
     if (mode == 2 && sq_err)
         CNB_CUDA_TRY(cudaMemsetAsync(sq_err, 0, sizeof(float) * (size_t)(rays->n_rays / rays->rays_per_segment), st));
@@ -1437,7 +1480,7 @@ int render_backward(const cnb_net_config* cfg, const float* const* P, const void
         float* o_rgb = rgb ? rgb : w.ray_rgb - r0 * 3;
         float* o_depth = depth ? depth : w.ray_depth - r0;
         float* o_acc = acc ? acc : w.ray_acc - r0;
-        CNB_TRY(launch_render_rays(cfg, P, packed, pl, rays, r0, nr, w.fw.folded, w.spill_sig, w.spill_rgb, o_rgb, o_depth,
+        CNB_TRY(launch_render_rays(cfg, P, packed, pl, rays, r0, nr, w.fw.folded, w.fw.rows, w.spill_sig, w.spill_rgb, o_rgb, o_depth,
                                    o_acc, st));
         const float* seed_rgb; const float* seed_depth = nullptr;
         if (mode == 2) {
@@ -1474,7 +1517,7 @@ int cnb_sm100_mlp_backward(const cnb_net_config* cfg, const float* const* P, con
     Plan pl;
     CNB_TRY(make_plan(cfg, P, &pl));
     if (n_codes > 1 && (samples_per_code % kTileRows) != 0) return CNB_E_UNSUPPORTED;
-    const int64_t sub_rows = S < kMaxSubTiles * kTileRows ? S : kMaxSubTiles * kTileRows;
+    const int64_t sub_rows = sm100::sub_batch_rays(1, S);      // rows are "rays of one sample": whole waves of tiles
     BwdWorkspace w;
     const int64_t n_sub = sub_rows > 0 ? (S + sub_rows - 1) / sub_rows : 1;
     int nbuf = (pipeline_wanted() && n_sub > 1) ? 2 : 1;
@@ -1489,6 +1532,10 @@ int cnb_sm100_mlp_backward(const cnb_net_config* cfg, const float* const* P, con
     Pipeline pipe;
     CNB_TRY(pipeline_begin(pipe, n_sub, d_params != nullptr));
     CNB_TRY(latent_and_fold(cfg, P, shape_codes, tex_codes, n_codes, w.fw, st));
+#if CNB_K2_BIAS_CONST || CNB_K2_HEADS_CONST
+    ConstRowsScope crs;
+    CNB_TRY(crs.begin(cfg, P, pl, w.fw.rows, st));
+#endif
     CNB_CUDA_TRY(cudaMemsetAsync(w.colsum, 0, sizeof(float) * (size_t)n_codes * pl.n_layers * kW, st));
     int sub = 0;
     for (int64_t r0 = 0; r0 < S; r0 += sub_rows, ++sub) {

@@ -31,6 +31,10 @@ extern std::atomic<long long> g_cnb_launches;
         if (_e != cudaSuccess) return (int)_e;              \
     } while (0)
 
+// Tuning / experiment switches (cnb_set_option in the C ABI).  Lookup order: a value set through cnb_set_option,
+// else the environment variable CNB_<NAME> (upper case), else `dflt`.  Read at launch time.
+int64_t cnb_option(const char* name, int64_t dflt);
+
 // Optional per-kernel CUDA-event timing (bench.py's roofline leg); no-ops unless enabled.
 enum { CNB_K_FWD = 0, CNB_K_BWD = 1, CNB_K_WGRAD = 2, CNB_K_COUNT = 3 };
 void cnb_prof_begin(int kernel_id, cudaStream_t st);

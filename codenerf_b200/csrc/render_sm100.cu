@@ -23,6 +23,13 @@ extern "C" int cnb_debug_trace(unsigned long long* out32, int reset) {
 }
 #endif
 
+// 1: K1 reads the launch-wide bias rows and the head weights from constant memory (sm100_common.cuh, ConstRows);
+// 0: from shared memory like the per-code rows.  Measured (round 2, A/B in one session, 30 steps): constant memory is
+// slower, 17.0-18.0 vs 18.3-18.8 M rays/s -- the uniform loads are served at a lower rate than LDS broadcasts.
+#ifndef CNB_K1_CONST
+#define CNB_K1_CONST 0
+#endif
+
 namespace {
 
 struct FwdParams {
@@ -471,21 +478,40 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                 const float* bias = L.folded >= 0 ? p.folded + ((size_t)code_b * p.n_folded + L.folded) * kW : L.bias;
                 float2 bias2 = make_float2(0.f, 0.f);
                 const bool mine = 2 * tg < L.n_halves * 128;
-                if (staged && mine) bias2 = __ldg(reinterpret_cast<const float2*>(bias) + tg);    // in flight during the wait
+                if (staged && mine && (L.folded >= 0 || !CNB_K1_CONST)) bias2 = __ldg(reinterpret_cast<const float2*>(bias) + tg);    // in flight during the wait
                 if (l == nl - 2) prepare_tile(t + 2, pe);      // next tile of this group: its PE is computed inside this wait
                 CNB_TR(tr_wacc, umma::mbar_wait(&acc_full[g], (uint32_t)(r * nl + l) & 1u));
                 const long long tr_p0 = CNB_TR_NOW();
                 umma::tc_fence_after();
-                if (staged) {
+                if (staged && !CNB_K1_CONST) {
                     float* sb = sBias + (g * 2 + bsel) * kW; bsel ^= 1u;
                     if (mine) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
                     const uint32_t tok = bar_sync_token(1 + g, 128);
                     const float* bs = smem_fptr(sb, tok);
                     const float* ws = smem_fptr(sWsig, tok);
                     const float* wr = smem_fptr(sWrgb, tok);
-                    if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
-                    else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
-                    else fwd_epilogue_layer<4, 2, false, false, true>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                    if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false, 1>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                    else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false, 1>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                    else fwd_epilogue_layer<4, 2, false, false, 1>(taddr, bs, a8, ws, wr, hacc, nullptr);
+                } else if (staged) {
+                    // head weights and the bias rows of the layers that are not code-conditioned: constant memory
+                    // (uniform loads, no shared-memory wavefronts); a folded layer's per-code row is staged in shared memory
+                    const float* ws = crow_ptr(kCrowWsig);
+                    const float* wr = crow_ptr(kCrowWrgb);
+                    if (L.folded >= 0) {
+                        float* sb = sBias + (g * 2 + bsel) * kW; bsel ^= 1u;
+                        if (mine) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
+                        const uint32_t tok = bar_sync_token(1 + g, 128);
+                        fwd_epilogue_layer<8, 0, true, false, 1, 2>(taddr, smem_fptr(sb, tok), a8, ws, wr, hacc, nullptr);
+                    } else {
+                        // fixed constant-memory slots (crow_slot): immediate addresses, uniform loads
+                        if (L.kind == 0) {
+                            if (l == 0) fwd_epilogue_layer<8, 0, true, false, 2>(taddr, crow_ptr(kCrowBias + 0 * kW), a8, ws, wr, hacc, nullptr);
+                            else fwd_epilogue_layer<8, 0, true, false, 2>(taddr, crow_ptr(kCrowBias + 2 * kW), a8, ws, wr, hacc, nullptr);
+                        }
+                        else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false, 2>(taddr, crow_ptr(kCrowBias + 1 * kW), a8, ws, wr, hacc, nullptr);
+                        else fwd_epilogue_layer<4, 2, false, false, 2>(taddr, crow_ptr(kCrowBias + 3 * kW), a8, ws, wr, hacc, nullptr);
+                    }
                 } else {
                     if (L.kind == 0) fwd_epilogue_layer<8, 0, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
                     else if (L.kind == 1) fwd_epilogue_layer<8, 1, true, false>(taddr, bias, a8, p.w_sigma, p.w_rgb2, hacc, nullptr);
@@ -1030,8 +1056,14 @@ int latent_and_fold(const cnb_net_config* c, const float* const* P, const float*
 namespace {
 
 int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packed, const Plan& pl, FwdParams& fp,
-               int64_t total_rows, cudaStream_t st) {
+               int64_t total_rows, float* rows_staging, cudaStream_t st) {
     CnbLayout L; cnb_make_layout(c, &L);
+#if CNB_K1_CONST
+    ConstRowsScope crs;                    // launch-wide bias rows and head weights -> constant memory (until the launch below)
+    CNB_TRY(crs.begin(c, P, pl, rows_staging, st));
+#else
+    (void)rows_staging;
+#endif
     fp.n_layers = pl.n_layers;
     for (int i = 0; i < pl.n_layers; ++i) fp.layers[i] = pl.fwd[i];
     fp.packed = (const uint8_t*)packed;
@@ -1051,9 +1083,10 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     int64_t units = (total_rows + 2 * kTileRows - 1) / (2 * kTileRows);
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-    const int use_pairs = [] { const char* e = getenv("CNB_CTA_PAIRS"); return e ? atoi(e) : 0; }();      // read per launch (tests switch it)
+    const int use_pairs = (int)cnb_option("cta_pairs", 0);
     const char* form = getenv("CNB_FWD_KERNEL");       // "ts": the tensor-memory operand experiment (slower)
-    if (!use_pairs && form && form[0] == 't') {
+    const bool use_ts = cnb_option("fwd_kernel_ts", 0) != 0 || (form && form[0] == 't');
+    if (!use_pairs && use_ts) {
         int n_slots = kTsMaxSlots;
         auto need = [&](int slots) {
             return 1024 + (size_t)slots * kSlot + 2 * (size_t)kABlock + 2 * (size_t)kDirBlock + 2 * kTileRows * sizeof(float4) +
@@ -1072,7 +1105,7 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     const int mc = (grid == sms && !use_pairs) ? weight_multicast() : 1;
     const bool pairs = use_pairs && grid >= 2;
     if (pairs) { grid &= ~1; CNB_TRY(make_weight_maps(packed, pl.total_bytes, &fp.maps)); }
-    const int epi8 = [] { const char* e = getenv("CNB_EPI_WARPS"); return e && atoi(e) == 8 ? 1 : 0; }();
+    const int epi8 = cnb_option("epi_warps", 4) == 8 ? 1 : 0;
     const bool ew8 = epi8 && fp.stage_bias;       // the head exchange lives in the staging area
     void (*kern)(const FwdParams) = pairs ? (ew8 ? k_render_fwd<2, 1, 8> : k_render_fwd<2, 1, 4>)
                                     : mc == 4 ? k_render_fwd<1, 4> : mc == 2 ? k_render_fwd<1, 2>
@@ -1184,7 +1217,8 @@ int make_weight_maps(const void* packed, size_t bytes, WeightMaps* out) {
 // the optional per-sample spill by launch-relative row.
 int launch_render_rays(const cnb_net_config* cfg, const float* const* P, const void* packed, const Plan& pl,
                        const cnb_ray_batch* rays, int64_t ray_begin, int64_t ray_count, const float* folded,
-                       float* spill_sig, float* spill_rgb, float* rgb, float* depth, float* acc, cudaStream_t st) {
+                       float* rows_staging, float* spill_sig, float* spill_rgb, float* rgb, float* depth, float* acc,
+                       cudaStream_t st) {
     const int N = rays->n_samples;
     const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * N;
     FwdParams fp = {};
@@ -1193,7 +1227,7 @@ int launch_render_rays(const cnb_net_config* cfg, const float* const* P, const v
     fp.rows_per_code = rays->n_codes > 1 ? rows_per_code : rays->n_rays * N;
     fp.white_bg = rays->white_bg;
     fp.rgb = rgb; fp.depth = depth; fp.acc = acc; fp.spill_sig = spill_sig; fp.spill_rgb = spill_rgb;
-    return launch_fwd(cfg, P, packed, pl, fp, fp.S, st);
+    return launch_fwd(cfg, P, packed, pl, fp, fp.S, rows_staging, st);
 }
 }  // namespace sm100
 
@@ -1214,7 +1248,7 @@ int cnb_sm100_mlp_forward(const cnb_net_config* cfg, const float* const* P, cons
     fp.folded = w.folded; fp.n_codes = n_codes; fp.rows_per_code = samples_per_code > 0 ? samples_per_code : S;
     fp.sigmas = sigmas; fp.rgbs = rgbs;
     fp.rs.N = 1;
-    return launch_fwd(cfg, P, packed, pl, fp, S, st);
+    return launch_fwd(cfg, P, packed, pl, fp, S, w.rows, st);
 }
 
 int cnb_sm100_render(const cnb_net_config* cfg, const float* const* P, const void* packed, const cnb_ray_batch* rays,
@@ -1235,7 +1269,7 @@ int cnb_sm100_render(const cnb_net_config* cfg, const float* const* P, const voi
     if (((uintptr_t)ws & 255) != 0) return CNB_E_ALIGNMENT;
     carve_fwd(cfg, rays->n_codes, 0, (char*)ws, &w);
     CNB_TRY(latent_and_fold(cfg, P, rays->shape_codes, rays->texture_codes, rays->n_codes, w, st));
-    return launch_render_rays(cfg, P, packed, pl, rays, 0, rays->n_rays, w.folded, nullptr, nullptr, rgb, depth, acc, st);
+    return launch_render_rays(cfg, P, packed, pl, rays, 0, rays->n_rays, w.folded, w.rows, nullptr, nullptr, rgb, depth, acc, st);
 }
 
 int cnb_sm100_pipeline_timeouts(void) {

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include "umma.cuh"
 #include <type_traits>
+#include <mutex>
 
 namespace sm100 {
 
@@ -93,19 +94,50 @@ __device__ __forceinline__ void st_shared_v4_off(uint32_t addr, uint32_t a, uint
     asm volatile("st.shared.v4.b32 [%0 + %5], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d), "n"(kOff));
 }
 
-// Vector load of 4 floats that every lane reads from the same address (bias / head-weight rows).  SM = true: `p`
-// carries a shared-window address (see smem_fptr) and the load is an LDS broadcast; false: read-only global load.
+// ---- rows every thread reads at the same address: bias rows, head weights --------------------------------
+// A warp-wide LDS.128 of ONE address still costs four shared-memory wavefronts (128-bit accesses are served per
+// quarter warp), so a 256-float bias row costs each epilogue warp 256 wavefronts -- bias and head-weight
+// broadcasts were 60 % of the LSU wavefronts of K2 and ~17 % of its shared-memory pipe time (round-2 profile), and
+// that pipe looked like what bounds the kernels.  EXPERIMENT (opt-in at compile time, CNB_K1_CONST / CNB_K2_*_CONST;
+// measured slower, kept as a record): rows that are the same for the whole launch (biases of the layers that are
+// not code-conditioned, the sigma / rgb.2 head weights) live in CONSTANT memory: the loads become LDCU.128 into
+// uniform registers and FADD2 / FFMA2 take them as uniform operands, no shared-memory traffic at all.  Result:
+// K2 9.55 -> 10.5 ms, K1 18.5 -> 17.5 M rays/s; and skipping the bias adds altogether (CNB_EXPERIMENT_NOBIAS) leaves
+// K2 unchanged: the broadcasts are not on K2's critical path (its period is set by the weight ring).
+constexpr int kCrowSlots = 4;        // launch-wide bias rows: 0 encoding_xyz, 1 encoding_shape, 2 encoding_viewdir, 3 rgb.0
+struct ConstRows {
+    float bias[kCrowSlots][kW];      // fixed slots, so that every load has an immediate address (LDCU; a run-time
+                                     // layer index in a vector register turns them into per-thread LDC.64)
+    float w_sigma[kW];               // sigma.0.weight
+    float w_rgb2[3 * (kW / 2)];      // rgb.2.weight
+    float b_sigma, b_rgb2[3];
+};
+static __constant__ ConstRows c_rows;      // one copy per translation unit; uploaded by ConstRowsScope before the launches
+constexpr int kCrowBias = 0;
+constexpr int kCrowWsig = kCrowSlots * kW;
+constexpr int kCrowWrgb = kCrowWsig + kW;
+constexpr int kCrowBsig = kCrowWrgb + 3 * (kW / 2);
+__device__ __forceinline__ float crow(int idx) { return reinterpret_cast<const float*>(&c_rows)[idx]; }
+// "pointer" to float `idx` of c_rows for ld_vec4<2>: an index in disguise, never dereferenced
+__device__ __forceinline__ const float* crow_ptr(int idx) { return reinterpret_cast<const float*>((uintptr_t)idx << 2); }
+
+// Vector load of 4 floats that every lane reads from the same address.  SRC = 0: read-only global load; 1: `p`
+// carries a shared-window address (see smem_fptr), LDS broadcast; 2: `p` is crow_ptr(index), constant memory.
 // The global form misses the small L1 left beside 220 KB of shared memory, and 64 such loads per layer with the
 // few registers available to prefetch them were the dominant stall of the epilogues (ncu source view, round 1).
-template <bool SM>
+template <int SRC>
 __device__ __forceinline__ float4 ld_vec4(const float* p) {
-    if (SM) {
+    if (SRC == 1) {
         // not volatile, no memory clobber: the scheduler may hoist these well ahead of their use (the address carries
         // a data dependence on the barrier that published the staging buffer, see bar_sync_token)
         float4 v;
         asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
             : "r"((uint32_t)(uintptr_t)p));
         return v;
+    }
+    if (SRC == 2) {
+        const int idx = (int)((uintptr_t)p >> 2);
+        return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(&c_rows) + idx);
     }
     return __ldg(reinterpret_cast<const float4*>(p));
 }
@@ -130,7 +162,7 @@ struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 // the next operand, [ReLU sign bits for the backward].   KIND: 0 hidden, 1 encoding_shape
 // (+ sigma head, no ReLU), 2 rgb.0 (+ rgb head).   a8[c] = shared address of 16-byte chunk c of
 // this row inside K-block 0.
-template <int CC, int KIND, bool STORE, bool MASK, bool SM = false>
+template <int CC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC>
 __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const float* __restrict__ bias,
                                                const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr,
@@ -141,13 +173,18 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
     for (int j8 = 0; j8 < 4; ++j8) {
         constexpr int dummy = 0; (void)dummy;
         const int col = CC * 32 + j8 * 8;
-        const float4 b0 = ld_vec4<SM>(bias + col);
-        const float4 b1 = ld_vec4<SM>(bias + col + 4);
         uint64_t v[4];
+#ifdef CNB_EXPERIMENT_NOBIAS     // timing experiment only (wrong results): what the bias broadcasts cost
+        v[0] = pk2(rr[j8 * 8 + 0], rr[j8 * 8 + 1]); v[1] = pk2(rr[j8 * 8 + 2], rr[j8 * 8 + 3]);
+        v[2] = pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]); v[3] = pk2(rr[j8 * 8 + 6], rr[j8 * 8 + 7]);
+#else
+        const float4 b0 = ld_vec4<SRC>(bias + col);
+        const float4 b1 = ld_vec4<SRC>(bias + col + 4);
         v[0] = fadd2(pk2(rr[j8 * 8 + 0], rr[j8 * 8 + 1]), pk2f(b0.x, b0.y));
         v[1] = fadd2(pk2(rr[j8 * 8 + 2], rr[j8 * 8 + 3]), pk2f(b0.z, b0.w));
         v[2] = fadd2(pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]), pk2f(b1.x, b1.y));
         v[3] = fadd2(pk2(rr[j8 * 8 + 6], rr[j8 * 8 + 7]), pk2f(b1.z, b1.w));
+#endif
         if (MASK && RELU) {     // collect the sign bits of the pre-activations (column c -> bit 31 - c%32)
             uint32_t s8 = 0u;   // 8 bits per group: four short dependency chains instead of one 32-deep chain
 #pragma unroll
@@ -159,8 +196,8 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
             sgn = (sgn << 8) | s8;
         }
         if (KIND == 1) {        // sigma head on the fp32 feature (reference src/model.py:45)
-            const float4 w0 = ld_vec4<SM>(w_sigma + col);
-            const float4 w1 = ld_vec4<SM>(w_sigma + col + 4);
+            const float4 w0 = ld_vec4<HSRC>(w_sigma + col);
+            const float4 w1 = ld_vec4<HSRC>(w_sigma + col + 4);
             acc.sig2 = ffma2(v[0], pk2f(w0.x, w0.y), acc.sig2); acc.sig2 = ffma2(v[1], pk2f(w0.z, w0.w), acc.sig2);
             acc.sig2 = ffma2(v[2], pk2f(w1.x, w1.y), acc.sig2); acc.sig2 = ffma2(v[3], pk2f(w1.z, w1.w), acc.sig2);
         } else if (KIND == 2) { // rgb.2 on the fp32 hidden (reference src/model.py:52)
@@ -169,8 +206,8 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
             for (int i = 0; i < 4; ++i) { float lo, hi; unpk2(v[i], lo, hi); h[i] = pk2f(fmaxf(lo, 0.f), fmaxf(hi, 0.f)); }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float4 w0 = ld_vec4<SM>(w_rgb2 + k * (kW / 2) + col);
-                const float4 w1 = ld_vec4<SM>(w_rgb2 + k * (kW / 2) + col + 4);
+                const float4 w0 = ld_vec4<HSRC>(w_rgb2 + k * (kW / 2) + col);
+                const float4 w1 = ld_vec4<HSRC>(w_rgb2 + k * (kW / 2) + col + 4);
                 uint64_t& a = (k == 0) ? acc.r2 : (k == 1 ? acc.g2 : acc.b2);
                 a = ffma2(h[0], pk2f(w0.x, w0.y), a); a = ffma2(h[1], pk2f(w0.z, w0.w), a);
                 a = ffma2(h[2], pk2f(w1.x, w1.y), a); a = ffma2(h[3], pk2f(w1.z, w1.w), a);
@@ -188,7 +225,7 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
 
 // A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.  (Four in flight, with the registers that
 // setmaxnreg frees, measured no faster and leaves no room for the next tile's prefetched encodings.)
-template <int NCC, int KIND, bool STORE, bool MASK, bool SM = false>
+template <int NCC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                    const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
@@ -198,8 +235,8 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         umma::tmem_ld32(taddr + CC * 32, ra);
         umma::tmem_ld32(taddr + CC * 32 + 32, rb);
         umma::tmem_ld_wait();
-        fwd_epilogue32<CC, KIND, STORE, MASK, SM>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SM>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC, KIND, STORE, MASK, SRC, HSRC>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SRC, HSRC>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -212,7 +249,7 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
 // NC (2 or 4) consecutive 32-column chunks of a layer: one thread's share when two warps split the columns of a row.
 // Every pointer / address argument is pre-offset to the thread's first chunk (so the column half is a run-time
 // value and the code exists once); a8 must point at the K-block that receives the first chunk.
-template <int NC, int KIND, bool STORE, bool MASK, bool SM>
+template <int NC, int KIND, bool STORE, bool MASK, int SM>
 __device__ __forceinline__ void fwd_epilogue_chunks(uint32_t taddr, const float* __restrict__ bias, const uint32_t (&a8)[8],
                                                     const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
                                                     HeadAcc& acc, uint32_t* mscr) {
@@ -533,8 +570,7 @@ inline int make_plan(const cnb_net_config* c, const float* const* P, Plan* pl) {
 
 // CNB_WEIGHT_MCAST = 1 | 2 | 4: CTAs per cluster sharing one multicast weight stream (full-grid launches only).
 inline int weight_multicast(int dflt = 1) {
-    const char* e = getenv("CNB_WEIGHT_MCAST");      // read per launch: tests switch it inside one process
-    const int m = e ? atoi(e) : dflt;
+    const int m = (int)cnb_option("weight_mcast", dflt);      // read per launch: tests switch it inside one process
     return (m == 2 || m == 4) ? m : 1;
 }
 // Largest grid (a multiple of the cluster size) whose clusters are all co-resident: the kernels are persistent
@@ -551,7 +587,7 @@ inline int cluster_grid(K kern, cudaLaunchConfig_t* cfg, int csize, int* grid) {
     return CNB_OK;
 }
 
-struct FwdWorkspace { float *z, *folded; float4* samples; size_t bytes; };
+struct FwdWorkspace { float *z, *folded, *rows; float4* samples; size_t bytes; };
 
 inline size_t carve_fwd(const cnb_net_config* c, int n_codes, int64_t spill_samples, char* base, FwdWorkspace* w) {
     size_t off = 0;
@@ -560,11 +596,77 @@ inline size_t carve_fwd(const cnb_net_config* c, int n_codes, int64_t spill_samp
     FwdWorkspace x = {};
     x.z = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
     x.folded = (float*)take(sizeof(float) * (size_t)n_codes * nf * kW);
+    x.rows = (float*)take(sizeof(ConstRows));              // staging image of c_rows (ConstRowsScope)
     x.samples = (float4*)take(sizeof(float4) * (size_t)spill_samples);
     x.bytes = off;
     if (w) *w = x;
     return off;
 }
+
+// ---- upload of c_rows -------------------------------------------------------------------------------------
+struct RowPtrs {
+    const float* bias[kCrowSlots];
+    const float *w_sigma, *w_rgb2, *b_sigma, *b_rgb2;
+    int n_out[kCrowSlots];
+};
+// constant-memory slot of a layer with a launch-wide bias
+__host__ __device__ __forceinline__ int crow_slot(const FwdLayer& L, int l) { return L.kind == 1 ? 1 : L.kind == 2 ? 3 : (l == 0 ? 0 : 2); }
+static __global__ void k_gather_const_rows(const RowPtrs r, float* __restrict__ out) {
+    const int n = (int)(sizeof(ConstRows) / sizeof(float));
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float v = 0.f;
+        if (i < kCrowWsig) { const int l = i / kW, c = i % kW; if (r.bias[l] && c < r.n_out[l]) v = r.bias[l][c]; }
+        else if (i < kCrowWrgb) v = r.w_sigma[i - kCrowWsig];
+        else if (i < kCrowBsig) v = r.w_rgb2[i - kCrowWrgb];
+        else if (i == kCrowBsig) v = r.b_sigma[0];
+        else if (i < kCrowBsig + 4) v = r.b_rgb2[i - kCrowBsig - 1];
+        out[i] = v;
+    }
+}
+// The constant rows are per-module state shared by every launch of this translation unit's kernels.  A scope
+// (one per API call) serialises their users: it takes a host lock, makes the stream wait for the last kernel that read
+// the previous contents (possibly on another stream), gathers the rows from the parameter tensors into `staging`
+// (workspace) and copies them into c_rows on the stream; its destructor records the "last use" event after the
+// call's launches and releases the lock.  Kernels of different streams therefore never see each other's rows.
+struct ConstRowsShared { std::mutex mu; cudaEvent_t ev[16] = {}; bool made[16] = {}; };
+static ConstRowsShared g_crow;
+class ConstRowsScope {
+  public:
+    ConstRowsScope() = default;
+    ConstRowsScope(const ConstRowsScope&) = delete;
+    int begin(const cnb_net_config* c, const float* const* P, const Plan& pl, float* staging, cudaStream_t st) {
+        g_crow.mu.lock(); locked_ = true; st_ = st;
+        if (cudaGetDevice(&dev_) != cudaSuccess || dev_ < 0 || dev_ >= 16) return CNB_E_DEVICE;
+        if (!g_crow.made[dev_]) {
+            CNB_CUDA_TRY(cudaEventCreateWithFlags(&g_crow.ev[dev_], cudaEventDisableTiming));
+            g_crow.made[dev_] = true;
+        } else {
+            CNB_CUDA_TRY(cudaStreamWaitEvent(st, g_crow.ev[dev_], 0));
+        }
+        CnbLayout L; cnb_make_layout(c, &L);
+        RowPtrs r = {};
+        for (int l = 0; l < pl.n_layers; ++l) {
+            if (pl.fwd[l].folded >= 0) continue;
+            const int slot = crow_slot(pl.fwd[l], l);
+            r.bias[slot] = pl.fwd[l].bias;
+            r.n_out[slot] = pl.fwd[l].n_halves * 128;
+        }
+        r.w_sigma = P[L.i_sigma]; r.b_sigma = P[L.i_sigma + 1]; r.w_rgb2 = P[L.i_rgb2]; r.b_rgb2 = P[L.i_rgb2 + 1];
+        k_gather_const_rows<<<8, 256, 0, st>>>(r, staging);
+        CNB_LAUNCH_CHECK();
+        CNB_CUDA_TRY(cudaMemcpyToSymbolAsync(c_rows, staging, sizeof(ConstRows), 0, cudaMemcpyDeviceToDevice, st));
+        armed_ = true;
+        return CNB_OK;
+    }
+    ~ConstRowsScope() {
+        if (armed_) cudaEventRecord(g_crow.ev[dev_], st_);
+        if (locked_) g_crow.mu.unlock();
+    }
+  private:
+    bool locked_ = false, armed_ = false;
+    int dev_ = 0;
+    cudaStream_t st_ = nullptr;
+};
 
 // z_j = ReLU(latent layer_j(code)) and the folded per-code biases (defined in render_sm100.cu).
 int latent_and_fold(const cnb_net_config* c, const float* const* P, const float* shape_codes, const float* tex_codes,
@@ -576,7 +678,8 @@ int make_weight_maps(const void* packed, size_t bytes, WeightMaps* out);
 // K1 over a ray sub-range (defined in render_sm100.cu).
 int launch_render_rays(const cnb_net_config* cfg, const float* const* P, const void* packed, const Plan& pl,
                        const cnb_ray_batch* rays, int64_t ray_begin, int64_t ray_count, const float* folded,
-                       float* spill_sig, float* spill_rgb, float* rgb, float* depth, float* acc, cudaStream_t st);
+                       float* rows_staging, float* spill_sig, float* spill_rgb, float* rgb, float* depth, float* acc,
+                       cudaStream_t st);
 // backward (defined in backward_sm100.cu)
 size_t bwd_workspace_bytes(const cnb_net_config* cfg, int64_t S, int64_t n_rays, int N, int n_codes, int fused);
 int render_backward(const cnb_net_config* cfg, const float* const* P, const void* packed, const cnb_ray_batch* rays,

@@ -188,6 +188,17 @@ int cnb_profile_read(int kernel_id, float* ms, int cap);
  * context is in an error state for any other reason). */
 int cnb_debug_pipeline_timeouts(void);
 
+/* Tuning / experiment switches (process-global; read at launch time).  Lookup order: the value set here, else the
+ * environment variable CNB_<NAME> in upper case, else the built-in default.  None is needed for correct results.
+ *   sub_tiles      128-row tiles per backward sub-batch (default 8192; the training stash needs ~1 MB of workspace
+ *                  per tile, larger is faster; changes cnb_*_workspace_bytes)
+ *   bwd_pairs, cta_pairs, weight_mcast, epi_warps, fwd_kernel_ts, k3_overlap, k3_sms, k3_items_per_sm_x10
+ *                  opt-in kernel variants kept for measurement
+ * Returns CNB_E_INVALID for an unknown name. */
+int cnb_set_option(const char* name, int64_t value);
+int cnb_clear_option(const char* name);
+int64_t cnb_get_option(const char* name, int64_t default_value);
+
 /* Number of kernel launches this library has issued in this process (for bench.py's gpu_launches). */
 int64_t cnb_launch_count(void);
 
