@@ -77,6 +77,8 @@ struct BwdParams {
     uint32_t* mask_scratch;         // [grid][2 groups][1 + lookahead][n_layers][8][128]
     float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l
     int stash;                      // 1: stream operand tiles + dspre to HBM (training)
+    int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
+    int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
     uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
     uint8_t *stashA, *stashD;
     float* dspre;                   // [S] d(loss)/d(sigma pre-activation)
@@ -393,6 +395,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         auto phase = [&](int64_t tile, bool live, int phs) {
             CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
             const bool stash = p.stash && live;
+            if (p.stash_wrap > 0) tile %= p.stash_wrap;
             int blocks = 0, out_layer = -1;
             uint8_t* dst = nullptr;
             if (phs == 0) { blocks = 1; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[0]; }
@@ -406,12 +409,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             if (stash) {
                 // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
                 // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
-                const uint32_t piece = (uint32_t)blocks * (kABlock / 32);
-                umma::bulk_s2g_hint(dst + (size_t)lane * piece, sA + (size_t)lane * piece, piece, pol_stream);
-                if (phs == 0)
-                    umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot + lane * (kDirBlock / 32),
-                                        sA + 4 * kABlock + lane * (kDirBlock / 32), kDirBlock / 32, pol_stream);
-                umma::bulk_commit();
+                const uint32_t piece = (uint32_t)blocks * (kABlock / p.stash_lanes);
+                if (lane < p.stash_lanes) {
+                    umma::bulk_s2g_hint(dst + (size_t)lane * piece, sA + (size_t)lane * piece, piece, pol_stream);
+                    if (phs == 0)
+                        umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot + lane * (kDirBlock / p.stash_lanes),
+                                            sA + 4 * kABlock + lane * (kDirBlock / p.stash_lanes), kDirBlock / p.stash_lanes, pol_stream);
+                    umma::bulk_commit();
+                }
             }
             if (live && out_layer >= 0 && ((p.colsum_layers >> out_layer) & 1u) && lane < blocks * 8) {
                 int64_t code = 0;
@@ -615,14 +620,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     }
                     float sig_pre;
                     { float a0, a1; unpk2(hacc.sig2, a0, a1); sig_pre = a0 + a1; }
-                    const float x = sig_pre + crow(kCrowBsig);
+                    const float x = sig_pre + (CNB_K2_HEADS_CONST ? crow(kCrowBsig) : __ldg(p.b_sigma));
                     if (i & 1) x_odd = x; else x_even = x;
                     if (p.fuse_comp) {
                         // per-ray compositing, loss seed and compositing backward of every ray that ends in this tile
                         float a0, a1, cr, cg, cb;
-                        unpk2(hacc.r2, a0, a1); cr = a0 + a1 + crow(kCrowBsig + 1);
-                        unpk2(hacc.g2, a0, a1); cg = a0 + a1 + crow(kCrowBsig + 2);
-                        unpk2(hacc.b2, a0, a1); cb = a0 + a1 + crow(kCrowBsig + 3);
+                        unpk2(hacc.r2, a0, a1); cr = a0 + a1 + (CNB_K2_HEADS_CONST ? crow(kCrowBsig + 1) : __ldg(p.b_rgb2 + 0));
+                        unpk2(hacc.g2, a0, a1); cg = a0 + a1 + (CNB_K2_HEADS_CONST ? crow(kCrowBsig + 2) : __ldg(p.b_rgb2 + 1));
+                        unpk2(hacc.b2, a0, a1); cb = a0 + a1 + (CNB_K2_HEADS_CONST ? crow(kCrowBsig + 3) : __ldg(p.b_rgb2 + 2));
                         ring[((i & 1) << 7) + row] = make_float4(cnb_softplus(x), cr, cg, cb);
                         umma::named_bar_sync(1 + g, 128);
                         const int j_lo = (i * kTileRows) / N, j_hi = ((i + 1) * kTileRows) / N;      // rays of the unit ending in tile i
@@ -1227,6 +1232,8 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.xyz = xyz; bp.viewdir = viewdir; bp.S = S; bp.row_offset = row_offset;
     bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
     bp.mask_scratch = w.masks; bp.colsum = w.colsum;
+    bp.stash_wrap = cnb_option("stash_wrap", 0);
+    bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux
     // warps of K2 do it, and only for the folded layers (the latent-code gradients need nothing else)
@@ -1261,10 +1268,21 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
                         sizeof(float) * (4 * kW + (CNB_K2_HEADS_CONST ? 0 : kW + 3 * (kW / 2)));
     // CNB_WEIGHT_MCAST=2: clusters of 2 share one multicast weight stream (+2.5 % in K2 in a back-to-back run, within
     // the box-to-box noise of the bench: left opt-in)
-    const int use_pairs = (int)cnb_option("bwd_pairs", 0);
+    // CTA pairs by default (round 2): every CTA streams half of each weight chunk, so the 4-slot ring covers a whole
+    // layer and the MMA phase is no longer refill-bound (K2 9.35 -> 8.45 ms per 65,536-ray step, latent fit +5 %).
+    // Needed two fixes to pay off: remote arrives without cluster-scope release (umma.cuh) and the stash written
+    // as a few large bulk stores (below).  bwd_pairs = 0 selects the single-CTA kernel.
+    const int use_pairs = (int)cnb_option("bwd_pairs", 1);
     const bool pairs = use_pairs && grid == sms;
     const int mc = pairs ? 2 : (grid == sms ? weight_multicast() : 1);      // cluster size
     if (pairs) CNB_TRY(make_weight_maps(packed, pl.total_bytes, &bp.maps));
+    {   // Bulk stores per stashed operand image.  Single CTA: 32 pieces of 2 KB, so that the weight refills sharing the SM's
+        // copy engine slip in between (one 64 KB store ahead of a refill stalls the ring: 10.9 -> 9.35 ms in round 1).
+        // CTA pairs: the ring is not the limit any more and the epilogue waits for the store instead; two 32 KB
+        // pieces drain the buffer fastest (measured: 32 pieces 10.4 ms, 8: 8.57, 2: 8.44, 1: 8.49).
+        const int64_t sl = cnb_option("stash_lanes", pairs ? 2 : 32);
+        bp.stash_lanes = (sl == 1 || sl == 2 || sl == 4 || sl == 8 || sl == 16) ? (int)sl : 32;
+    }
     void (*kern)(const BwdParams) = pairs ? k_mlp_bwd<1, 2> : mc == 4 ? k_mlp_bwd<4> : mc == 2 ? k_mlp_bwd<2> : k_mlp_bwd<1>;
     CNB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};

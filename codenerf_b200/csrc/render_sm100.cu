@@ -1083,7 +1083,8 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     int64_t units = (total_rows + 2 * kTileRows - 1) / (2 * kTileRows);
     if (fp.mode == 0 && units > fp.n_rays) units = fp.n_rays;
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
-    const int use_pairs = (int)cnb_option("cta_pairs", 0);
+    // CTA pairs by default (round 2, with the light-weight remote arrives of umma.cuh): +8-13 % in a same-session A/B
+    const int use_pairs = (int)cnb_option("cta_pairs", 1);
     const char* form = getenv("CNB_FWD_KERNEL");       // "ts": the tensor-memory operand experiment (slower)
     const bool use_ts = cnb_option("fwd_kernel_ts", 0) != 0 || (form && form[0] == 't');
     if (!use_pairs && use_ts) {

@@ -177,14 +177,21 @@ __device__ __forceinline__ void cluster_sync_all() {
 __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
     uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank)); return r;
 }
+// Remote arrive on an mbarrier of another CTA of the cluster (address from mapa).  Default semantics (release at CTA
+// scope), as CUTLASS's ClusterBarrier::arrive does: an explicit `.release.cluster` compiles to MEMBAR.ALL.GPU +
+// CCTL.IVALL -- a GPU-scope fence that waits for every outstanding global store of the thread (the ReLU mask words,
+// the stash) and an invalidation of the SM's whole L1 -- on EVERY operand hand-off; that, not shared-memory
+// bandwidth, is what made the CTA-pair kernels' epilogues slow in round 1.  What the hand-off needs is already
+// there: the operand stores are fenced into the async proxy (fence.proxy.async) and read by this CTA's own tensor
+// core; the arrive only tells the leader that it may issue.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"      // default acquire.cta: `.acquire.cluster` costs a CCTL.IVALL per wait
         "selp.b32 %0, 1, 0, P;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;

@@ -5,8 +5,10 @@ variants = sys.argv[1:] or [""]
 for rnd in range(2):
     for v in variants:
         env = dict(os.environ)
-        if v: env["CNB_LIB"] = v
-        else: env.pop("CNB_LIB", None)
+        env.pop("CNB_LIB", None)
+        for part in v.split(","):             # "libsuffix" and / or "NAME=VALUE" environment switches, comma separated
+            if "=" in part: k, x = part.split("=", 1); env[k] = x
+            elif part: env["CNB_LIB"] = part
         out = subprocess.run([sys.executable, "bench.py", "--steps", os.environ.get("AB_STEPS", "10"), "--warmup", "3", "--no-cpu-baseline", "--quick"], env=env,
                              capture_output=True, text=True, cwd=root)
         try:

@@ -109,10 +109,12 @@ def test_backward_is_linear_in_the_seed():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("env", [{"CNB_BWD_PAIRS": "1"}, {"CNB_WEIGHT_MCAST": "2"}, {"CNB_K3_OVERLAP": "1"}],
-                         ids=["cta-pairs", "multicast2", "k3-overlap"])
+@pytest.mark.parametrize("env", [{"CNB_BWD_PAIRS": "0"}, {"CNB_WEIGHT_MCAST": "2", "CNB_BWD_PAIRS": "0"}, {"CNB_K3_OVERLAP": "1"},
+                                 {"CNB_STASH_LANES": "32"}],
+                         ids=["single-cta", "multicast2", "k3-overlap", "stash-2KB-pieces"])
 def test_backward_kernel_variants_match_default(env):
-    """The opt-in forms of the training step (measured, not faster) give the default's gradients."""
+    """The other forms of the training step (measured, not faster than the default CTA-pair kernel) give
+    the default's gradients."""
     from codenerf_b200 import _lib, ops
     model, t, bundle = _batch()
     params = model.param_list(); packed = model._packed.get(model._cfg, params)
