@@ -748,6 +748,8 @@ struct WgProblem {
     uint8_t n_blocks;     // input width / 64 (1 or 4)
     uint8_t is_dir;       // input is the [128 x 32] PE(viewdir) block (64-B swizzle)
     uint8_t layer;        // fwd layer of dY_l: slot of its column sums (bias / latent-code gradients); 0xff: none
+    uint8_t sigma;        // the staged input is f (encoding_viewdir's input): the flush warps also reduce the sigma-head
+                          // weight gradient sum_rows dspre[row] * f[row][:] from it (the head kernel need not re-read f)
     int32_t splits;       // work items this problem is cut into (along rows)
     int32_t item0;        // index of its first work item
 };
@@ -761,6 +763,9 @@ struct WgParams {
     float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l (reduced here from the staged tiles)
     int n_layers, n_codes;
     int64_t rows_per_code, row_offset;
+    const float* dspre;             // [S] d(loss)/d(sigma pre-activation), launch-relative rows
+    int64_t S;
+    float *d_wsigma, *d_bsigma;     // sigma.0.weight / bias gradients (accumulated)
 };
 constexpr int kWgStage = 65536;      // 64 rows: dY half-blocks [0, 32 KB) + input half-blocks [32 KB, 64 KB)
 constexpr int kWgStages = 3;
@@ -870,9 +875,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
             const WgProblem& P = p.prob[pi];
             // ---- column sums of dY_l from the staged half-tiles (bias and latent-code gradients) ----
             const bool reduce = P.layer != 0xff && wq < P.m_blocks;
-            float cs[8];
+            const bool sigma = P.sigma != 0;           // input blocks are f: 4 blocks, one per flush warp
+            float cs[8], sg[8], sgb = 0.f;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) cs[i] = 0.f;
+            for (int i = 0; i < 8; ++i) { cs[i] = 0.f; sg[i] = 0.f; }
             int64_t cur_code = -1;
             auto flush_cs = [&]() {
                 if (cur_code < 0) return;
@@ -891,29 +897,67 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
             };
             for (int64_t h = hb; h < he; ++h) {
                 umma::mbar_wait(&full[stage], ph);
-                if (reduce) {
+                if (reduce || sigma) {
                     int64_t code = 0;
                     if (p.n_codes > 1) { code = (p.row_offset + (h >> 1) * kTileRows) / p.rows_per_code; if (code >= p.n_codes) code = p.n_codes - 1; }
-                    if (code != cur_code) { flush_cs(); cur_code = code; }
+                    if (reduce && code != cur_code) { flush_cs(); cur_code = code; }
                     const uint8_t* base = smem + stage * kWgStage + wq * 8192;
-                    uint4 w[16];                  // load first, release the stage, then add
+                    uint4 w[16], wf[16];          // load first, release the stage, then add
+                    float dsp[16];
+                    if (reduce) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int rr = rg * 16 + i;
-                        w[i] = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                        for (int i = 0; i < 16; ++i) {
+                            const int rr = rg * 16 + i;
+                            w[i] = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                        }
+                    }
+                    if (sigma) {
+                        const int64_t r0 = h * 64 + rg * 16;       // launch-relative row of this lane's first row in the half-tile
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const int rr = rg * 16 + i;
+                            wf[i] = ld_shared_v4(base + 32768 + rr * 128 + ((chunk ^ (rr & 7)) << 4));
+                            dsp[i] = (r0 + i < p.S) ? __ldg(p.dspre + r0 + i) : 0.f;
+                        }
                     }
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&empty[stage]);
+                    if (reduce) {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        cs[0] += bf_lo(w[i].x); cs[1] += bf_hi(w[i].x); cs[2] += bf_lo(w[i].y); cs[3] += bf_hi(w[i].y);
-                        cs[4] += bf_lo(w[i].z); cs[5] += bf_hi(w[i].z); cs[6] += bf_lo(w[i].w); cs[7] += bf_hi(w[i].w);
+                        for (int i = 0; i < 16; ++i) {
+                            cs[0] += bf_lo(w[i].x); cs[1] += bf_hi(w[i].x); cs[2] += bf_lo(w[i].y); cs[3] += bf_hi(w[i].y);
+                            cs[4] += bf_lo(w[i].z); cs[5] += bf_hi(w[i].z); cs[6] += bf_lo(w[i].w); cs[7] += bf_hi(w[i].w);
+                        }
+                    }
+                    if (sigma) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            sg[0] = fmaf(dsp[i], bf_lo(wf[i].x), sg[0]); sg[1] = fmaf(dsp[i], bf_hi(wf[i].x), sg[1]);
+                            sg[2] = fmaf(dsp[i], bf_lo(wf[i].y), sg[2]); sg[3] = fmaf(dsp[i], bf_hi(wf[i].y), sg[3]);
+                            sg[4] = fmaf(dsp[i], bf_lo(wf[i].z), sg[4]); sg[5] = fmaf(dsp[i], bf_hi(wf[i].z), sg[5]);
+                            sg[6] = fmaf(dsp[i], bf_lo(wf[i].w), sg[6]); sg[7] = fmaf(dsp[i], bf_hi(wf[i].w), sg[7]);
+                            if (wq == 0 && chunk == 0) sgb += dsp[i];
+                        }
                     }
                 } else {
                     __syncwarp();
                     if (lane == 0) umma::mbar_arrive(&empty[stage]);
                 }
                 if (++stage == kWgStages) { stage = 0; ph ^= 1; }
+            }
+            if (sigma) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    sg[i] += __shfl_xor_sync(0xffffffffu, sg[i], 8);
+                    sg[i] += __shfl_xor_sync(0xffffffffu, sg[i], 16);
+                }
+                sgb += __shfl_xor_sync(0xffffffffu, sgb, 8);
+                sgb += __shfl_xor_sync(0xffffffffu, sgb, 16);
+                if (rg == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) atomicAdd(p.d_wsigma + wq * 64 + chunk * 8 + i, sg[i]);
+                    if (wq == 0 && chunk == 0) atomicAdd(p.d_bsigma, sgb);
+                }
             }
             if (reduce) flush_cs();
             umma::mbar_wait(acc_done, it & 1u);
@@ -943,96 +987,111 @@ __global__ void __launch_bounds__(kWgThreads, 1) k_wgrad(const __grid_constant__
 }
 
 // ---------------------------------------------------------------------------
-// Narrow-head weight gradients from the stash: d(sigma.weight) = sum dspre * f, d(rgb.2.weight) = sum d_rgb (x) r1,
-// and their biases.  Thread t owns column t; rows are streamed tile by tile.
-__global__ void k_head_wgrad(const uint8_t* __restrict__ stashA, uint32_t a_tile_bytes, uint32_t f_off, uint32_t r1_off,
-                             const float* __restrict__ dspre, const float* __restrict__ d_rgbs, int64_t S,
-                             int64_t n_tiles, float* __restrict__ d_wsigma, float* __restrict__ d_bsigma,
+// rgb.2 weight / bias gradients from the stash: d(rgb.2.weight) = sum d_rgb (x) r1.  (The sigma head's gradient is
+// reduced inside K3, whose encoding_viewdir problem stages the sigma head's input anyway.)  A pure HBM stream
+// (32 KB per tile): every warp takes 16 KB block images of r1 (the rgb.2 input, 128 wide: two blocks per tile) and
+// reads them with fully coalesced 512-byte loads, eight in flight.  Load i of a block gives lane l the 16-byte chunk
+// at position l & 7 of row 4 i + (l >> 3); with the 128-byte swizzle that is logical chunk (l & 7) ^ (row & 7), which
+// for a fixed lane alternates between two values with the parity of i: two accumulator sets per lane, reduced across
+// CTAs with atomics at the end.
+constexpr int kHeadWarps = 8;
+__global__ void __launch_bounds__(kHeadWarps * 32) k_head_wgrad(const uint8_t* __restrict__ stashA, uint32_t a_tile_bytes, uint32_t r1_off,
+                             const float* __restrict__ d_rgbs, int64_t S, int64_t n_tiles,
                              float* __restrict__ d_wrgb2, float* __restrict__ d_brgb2) {
-    // 8 warps; warp w streams rows w, w+8, ... of each tile.  Lane l owns one 16-byte chunk (8 columns) of the
-    // row: f chunk (blk = l>>3, chunk = l&7) and, for lanes < 16, the r1 chunk at the same coordinates.
-    __shared__ float red[8][32][33];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int blk = lane >> 3, chunk = lane & 7;
-    float af[8], ar[8], ag[8], ab[8];
+    const int blk = warp & 1;                   // which of the tile's two r1 blocks this warp reads
+    const int rsub = lane >> 3, pos = lane & 7;
+    float acc[2][3][8];            // [row parity class][r, g, b][8 columns of the chunk]
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { af[i] = 0.f; ar[i] = 0.f; ag[i] = 0.f; ab[i] = 0.f; }
-    float bs = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const uint8_t* base = stashA + (size_t)tile * a_tile_bytes;
-        const int rows = (int)min((int64_t)kTileRows, S - tile * kTileRows);
-        for (int r0 = warp; r0 < rows; r0 += 32) {        // 4 rows in flight per warp
-            uint4 fw[4], rw[4]; float dsp[4], dr[4], dg[4], db[4];
+    for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int r = r0 + u * 8;
-                const bool ok = r < rows;
-                const int64_t gr = tile * kTileRows + (ok ? r : 0);
-                const uint32_t off = blk * kABlock + (ok ? r : 0) * 128 + ((chunk ^ (r & 7)) << 4);
-                fw[u] = __ldg(reinterpret_cast<const uint4*>(base + f_off + off));
-                rw[u] = lane < 16 ? __ldg(reinterpret_cast<const uint4*>(base + r1_off + off)) : make_uint4(0, 0, 0, 0);
-                dsp[u] = ok ? __ldg(dspre + gr) : 0.f;
-                dr[u] = ok ? __ldg(d_rgbs + gr * 3) : 0.f; dg[u] = ok ? __ldg(d_rgbs + gr * 3 + 1) : 0.f;
-                db[u] = ok ? __ldg(d_rgbs + gr * 3 + 2) : 0.f;
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[a][k][j] = 0.f;
+    float bsum[3] = {0.f, 0.f, 0.f};            // bias gradient: block-0 warps, lanes with pos == 0
+    const int64_t tstride = (int64_t)gridDim.x * (kHeadWarps / 2);
+    for (int64_t tile = (int64_t)blockIdx.x * (kHeadWarps / 2) + (warp >> 1); tile < n_tiles; tile += tstride) {
+        const uint4* src = reinterpret_cast<const uint4*>(stashA + (size_t)tile * a_tile_bytes + r1_off + (size_t)blk * kABlock) + lane;
+        const int64_t row0 = tile * kTileRows;
+#pragma unroll
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+            uint4 w[8]; float s0[8], s1[8], s2[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int64_t r = row0 + 4 * (i0 + u) + rsub;
+                const bool ok = r < S;
+                w[u] = __ldcs(src + (size_t)(i0 + u) * 32);          // streaming: every byte is read once
+                s0[u] = ok ? __ldg(d_rgbs + r * 3) : 0.f; s1[u] = ok ? __ldg(d_rgbs + r * 3 + 1) : 0.f; s2[u] = ok ? __ldg(d_rgbs + r * 3 + 2) : 0.f;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                af[0] = fmaf(dsp[u], bf_lo(fw[u].x), af[0]); af[1] = fmaf(dsp[u], bf_hi(fw[u].x), af[1]);
-                af[2] = fmaf(dsp[u], bf_lo(fw[u].y), af[2]); af[3] = fmaf(dsp[u], bf_hi(fw[u].y), af[3]);
-                af[4] = fmaf(dsp[u], bf_lo(fw[u].z), af[4]); af[5] = fmaf(dsp[u], bf_hi(fw[u].z), af[5]);
-                af[6] = fmaf(dsp[u], bf_lo(fw[u].w), af[6]); af[7] = fmaf(dsp[u], bf_hi(fw[u].w), af[7]);
-                const float h[8] = {bf_lo(rw[u].x), bf_hi(rw[u].x), bf_lo(rw[u].y), bf_hi(rw[u].y),
-                                    bf_lo(rw[u].z), bf_hi(rw[u].z), bf_lo(rw[u].w), bf_hi(rw[u].w)};
+            for (int u = 0; u < 8; ++u) {
+                const float h[8] = {bf_lo(w[u].x), bf_hi(w[u].x), bf_lo(w[u].y), bf_hi(w[u].y),
+                                    bf_lo(w[u].z), bf_hi(w[u].z), bf_lo(w[u].w), bf_hi(w[u].w)};
+                const int a = u & 1;                      // parity of the load index = parity class of the row
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { ar[i] = fmaf(dr[u], h[i], ar[i]); ag[i] = fmaf(dg[u], h[i], ag[i]); ab[i] = fmaf(db[u], h[i], ab[i]); }
-                if (lane == 0) { bs += dsp[u]; b0 += dr[u]; b1 += dg[u]; b2 += db[u]; }
+                for (int j = 0; j < 8; ++j) {
+                    acc[a][0][j] = fmaf(s0[u], h[j], acc[a][0][j]); acc[a][1][j] = fmaf(s1[u], h[j], acc[a][1][j]);
+                    acc[a][2][j] = fmaf(s2[u], h[j], acc[a][2][j]);
+                }
+                if (pos == 0 && blk == 0) { bsum[0] += s0[u]; bsum[1] += s1[u]; bsum[2] += s2[u]; }
             }
         }
     }
-    // cross-warp reduction: value slot v of lane l -> red[warp][l][v]
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        red[warp][lane][i] = af[i]; red[warp][lane][8 + i] = ar[i];
-        red[warp][lane][16 + i] = ag[i]; red[warp][lane][24 + i] = ab[i];
-    }
+    // CTA-level reduction in shared memory first: same-address atomics are served one at a time by the L2 (straight global
+    // atomics from every lane, 3.6 M on 384 addresses, cost 1 ms); then 387 global atomics per CTA
+    __shared__ float red[3 * (kW / 2) + 4];
+    for (int i = threadIdx.x; i < 3 * (kW / 2) + 4; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
-    for (int o = threadIdx.x; o < 32 * 32; o += blockDim.x) {
-        const int l = o >> 5, v = o & 31;
-        float s = 0.f;
+    // logical chunk of parity class a: pos ^ ((4 a + rsub) & 7)
 #pragma unroll
-        for (int w = 0; w < 8; ++w) s += red[w][l][v];
-        const int col = (l >> 3) * 64 + (l & 7) * 8 + (v & 7);
-        if (v < 8) atomicAdd(d_wsigma + col, s);
-        else if (l < 16) atomicAdd(d_wrgb2 + ((v >> 3) - 1) * 128 + col, s);
+    for (int a = 0; a < 2; ++a) {
+        const int chunk = pos ^ ((4 * a + rsub) & 7);
+        const int col = blk * 64 + chunk * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(red + 0 * (kW / 2) + col + j, acc[a][0][j]);
+            atomicAdd(red + 1 * (kW / 2) + col + j, acc[a][1][j]);
+            atomicAdd(red + 2 * (kW / 2) + col + j, acc[a][2][j]);
+        }
     }
-    if (lane == 0) { atomicAdd(d_bsigma, bs); atomicAdd(d_brgb2, b0); atomicAdd(d_brgb2 + 1, b1); atomicAdd(d_brgb2 + 2, b2); }
+    if (pos == 0 && blk == 0) { atomicAdd(red + 3 * (kW / 2), bsum[0]); atomicAdd(red + 3 * (kW / 2) + 1, bsum[1]); atomicAdd(red + 3 * (kW / 2) + 2, bsum[2]); }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * (kW / 2); i += blockDim.x) atomicAdd(d_wrgb2 + i, red[i]);
+    if (threadIdx.x < 3) atomicAdd(d_brgb2 + threadIdx.x, red[3 * (kW / 2) + threadIdx.x]);
 }
 
-// Bias gradients: db_l[n] += sum_codes colsum[code][l][n].
-__global__ void k_bias_from_colsum(const float* __restrict__ colsum, int n_codes, int nl, int l, int n_out,
-                                   float* __restrict__ db) {
+// Bias gradients of every layer in one launch: db_l[n] += sum_codes colsum[code][l][n]  (blockIdx.y = layer).
+struct BiasOut { float* db[kMaxLayers]; int n_out[kMaxLayers]; };
+__global__ void k_bias_from_colsum(const float* __restrict__ colsum, int n_codes, int nl, const BiasOut o) {
+    const int l = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= n_out) return;
+    if (n >= o.n_out[l]) return;
     float a = 0.f;
     for (int c = 0; c < n_codes; ++c) a += colsum[((size_t)c * nl + l) * kW + n];
-    db[n] += a;
+    o.db[l][n] += a;
 }
 
-// Folded layers: dz[code][k] = sum_n cs[code][n] W[n][k]  (gradient reaching the latent branch output),
-// and the rank-1 weight term the fold moved out of the GEMM: dW[n][k] += cs[code][n] * z[code][k].
+// Folded layers: dz[code][k] = sum_n cs[code][n] W[n][k]  (gradient reaching the latent branch output; blocks
+// [0, n_codes)), and the rank-1 weight term the fold moved out of the GEMM, summed over the codes without atomics:
+// dW[n][k] += sum_code cs[code][n] * z[code][k]  (blocks [n_codes, n_codes + 256): one dW row each; nothing else
+// writes dW at that point of the stream).
 __global__ void k_fold_bwd(const float* __restrict__ Wj, const float* __restrict__ cs /*[n_codes] stride cs_ld*/,
-                           int64_t cs_ld, const float* __restrict__ z, int64_t z_ld, float* __restrict__ dz,
+                           int64_t cs_ld, const float* __restrict__ z, int64_t z_ld, int n_codes, float* __restrict__ dz,
                            float* __restrict__ dW) {
-    const int code = blockIdx.x, k = threadIdx.x;      // 256 threads
-    const float* c = cs + (size_t)code * cs_ld;
-    const float zk = z[(size_t)code * z_ld + k];
-    float a = 0.f;
-    for (int n = 0; n < kW; ++n) {
-        const float cn = c[n];
-        a = fmaf(cn, __ldg(Wj + (size_t)n * kW + k), a);
-        if (dW && cn != 0.f) atomicAdd(dW + (size_t)n * kW + k, cn * zk);
+    const int k = threadIdx.x;      // 256 threads
+    if ((int)blockIdx.x < n_codes) {
+        const int code = blockIdx.x;
+        const float* c = cs + (size_t)code * cs_ld;
+        float a = 0.f;
+#pragma unroll 8
+        for (int n = 0; n < kW; ++n) a = fmaf(c[n], __ldg(Wj + (size_t)n * kW + k), a);
+        dz[(size_t)code * z_ld + k] = a;
+    } else if (dW) {
+        const int n = blockIdx.x - n_codes;
+        float a = 0.f;
+        for (int code = 0; code < n_codes; ++code) a = fmaf(cs[(size_t)code * cs_ld + n], z[(size_t)code * z_ld + k], a);
+        dW[(size_t)n * kW + k] += a;
     }
-    dz[(size_t)code * z_ld + k] = a;
 }
 
 // d_rgb seed of the fused training step (mean L2 over each segment, src/trainer.py:75).
@@ -1314,6 +1373,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         q.d_off = sl.d_slot[lay]; q.a_off = a_off; q.w_off = w_off; q.ld = ld; q.col0 = col0; q.n_valid = n_valid;
         q.m_blocks = (uint8_t)(pl.fwd[lay].n_halves * 2); q.n_blocks = (uint8_t)n_blocks; q.is_dir = (uint8_t)is_dir;
         q.layer = is_dir ? (uint8_t)0xff : (uint8_t)lay;      // each dY_l is reduced exactly once
+        q.sigma = (!is_dir && pl.fwd[lay].has_dir) ? 1 : 0;   // encoding_viewdir: its input is f, the sigma head's input
         wp.prob[np++] = q;
     };
     {
@@ -1343,6 +1403,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     wp.stashA = stashA; wp.stashD = stashD; wp.a_tile_bytes = sl.a_tile_bytes; wp.d_tile_bytes = sl.d_tile_bytes;
     wp.n_tiles = tiles; wp.dP = d_params;
     wp.colsum = w.colsum; wp.n_layers = nl; wp.n_codes = n_codes; wp.rows_per_code = rows_per_code; wp.row_offset = row_offset;
+    wp.dspre = dspre_buf; wp.S = S; wp.d_wsigma = d_params + L.sigma_w; wp.d_bsigma = d_params + L.sigma_b;
     const size_t wsmem = 1024 + (size_t)kWgStages * kWgStage + 256;
     CNB_CUDA_TRY(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     int wgrid = items < sms ? items : sms;
@@ -1351,12 +1412,11 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     k_wgrad<<<wgrid, kWgThreads, wsmem, st2>>>(wp);
     cnb_prof_end(CNB_K_WGRAD, st2);
     CNB_LAUNCH_CHECK();
-    // narrow heads (sigma, rgb.2): inputs f (input of encoding_viewdir) and the rgb.0 hidden
-    int l_vd = 1 + c->shape_blocks + 1;
-    const int hgrid = (int)(tiles < 6 * sms ? tiles : 6 * sms);
-    k_head_wgrad<<<hgrid, 256, 0, st2>>>(stashA, sl.a_tile_bytes, sl.a_slot[l_vd], sl.a_slot[nl], dspre_buf, d_rgbs, S, tiles,
-                                        d_params + L.sigma_w, d_params + L.sigma_b, d_params + L.rgb2_w,
-                                        d_params + L.rgb2_b);
+    // rgb.2 head: input r1 = the rgb.0 hidden (the sigma head is reduced inside K3)
+    const int64_t hwant = (tiles + kHeadWarps / 2 - 1) / (kHeadWarps / 2);
+    const int hgrid = (int)(hwant < 2 * sms ? hwant : 2 * sms);
+    k_head_wgrad<<<hgrid, kHeadWarps * 32, 0, st2>>>(stashA, sl.a_tile_bytes, sl.a_slot[nl], d_rgbs, S, tiles,
+                                                    d_params + L.rgb2_w, d_params + L.rgb2_b);
     CNB_LAUNCH_CHECK();
     if (piped) {
         CNB_CUDA_TRY(cudaEventRecord(pp->k3_done[buf], pp->st3));
@@ -1378,11 +1438,10 @@ int finish_bwd(const cnb_net_config* c, const float* const* P, const Plan& pl, B
         boff[l++] = L.enc_shape_b; boff[l++] = L.enc_vd_b;
         for (int j = 0; j < c->texture_blocks; ++j) boff[l++] = L.t_b[j];
         boff[l++] = L.rgb0_b;
-        for (int i = 0; i < nl; ++i) {
-            const int n_out = pl.fwd[i].n_halves * 128;
-            k_bias_from_colsum<<<(n_out + 127) / 128, 128, 0, st>>>(w.colsum, n_codes, nl, i, n_out, d_params + boff[i]);
-            CNB_LAUNCH_CHECK();
-        }
+        BiasOut bo = {};
+        for (int i = 0; i < nl; ++i) { bo.db[i] = d_params + boff[i]; bo.n_out[i] = pl.fwd[i].n_halves * 128; }
+        k_bias_from_colsum<<<dim3(2, nl), 128, 0, st>>>(w.colsum, n_codes, nl, bo);
+        CNB_LAUNCH_CHECK();
     }
     CNB_CUDA_TRY(cudaMemsetAsync(d_shape, 0, sizeof(float) * (size_t)n_codes * c->latent_dim, st));
     CNB_CUDA_TRY(cudaMemsetAsync(d_tex, 0, sizeof(float) * (size_t)n_codes * c->latent_dim, st));
@@ -1397,8 +1456,8 @@ int finish_bwd(const cnb_net_config* c, const float* const* P, const Plan& pl, B
         const int64_t w_off = shape ? L.s_w[jj] : L.t_w[jj];
         const int64_t lw_off = shape ? L.sl_w[jj] : L.tl_w[jj];
         const int64_t lb_off = shape ? L.sl_b[jj] : L.tl_b[jj];
-        k_fold_bwd<<<n_codes, kW, 0, st>>>(P[iw], w.colsum + (size_t)l * kW, (int64_t)nl * kW, w.fw.z + (size_t)j * kW, zld,
-                                          w.dz + (size_t)j * kW, d_params ? d_params + w_off : nullptr);
+        k_fold_bwd<<<n_codes + (d_params ? kW : 0), kW, 0, st>>>(P[iw], w.colsum + (size_t)l * kW, (int64_t)nl * kW, w.fw.z + (size_t)j * kW,
+                                                                zld, n_codes, w.dz + (size_t)j * kW, d_params ? d_params + w_off : nullptr);
         CNB_LAUNCH_CHECK();
         CNB_TRY(cnb_launch_latent_bwd(P[il], shape ? shape_codes : tex_codes, w.fw.z + (size_t)j * kW, w.dz + (size_t)j * kW,
                                       zld, n_codes, c->latent_dim, kW, d_params ? d_params + lw_off : nullptr,
