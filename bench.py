@@ -451,7 +451,8 @@ def run_ours(args):
     I = make_inputs(N)
     ms_step, launches, kt, clocks = timed(lambda: step(I, I["c2w"], I["z"], I["tgt"]), args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _, _, _ = timed(lambda: step_e2e(I), args.steps, max(1, args.warmup // 2))
-    ms_fwd, _, kt_f, _ = timed(lambda: fwd_only(I), args.steps, 2)
+    fwd_steps = max(args.steps, 20)      # a forward step is 3.5 ms: more of them for a stable number
+    ms_fwd, _, kt_f, _ = timed(lambda: fwd_only(I), fwd_steps, 3)
     d_seed = I["tgt"] * 1e-4            # any per-ray d_rgb: the latent-fit leg times the kernels only
     ms_lat, _, _, _ = timed(lambda: latent_only(I, d_seed), args.steps, 2)
     extra = {}
@@ -502,7 +503,7 @@ def run_ours(args):
         e2e = total_rays / (ms_e2e * 1e-3)
         samples = n_rays * N
         roofs = roofline_entries(kt, args.steps, samples, peaks, clocks, n_obj, N)
-        roofs.update(roofline_entries({k: v for k, v in kt_f.items() if k == "fwd"}, args.steps, samples, peaks, clocks, n_obj, N))
+        roofs.update(roofline_entries({k: v for k, v in kt_f.items() if k == "fwd"}, fwd_steps, samples, peaks, clocks, n_obj, N))
         kmean = {k: float(np.sum(v)) / args.steps for k, v in kt.items()}     # ms per step
         dom = max(kmean, key=kmean.get) if kmean else None
         roof = dict(roofs[dom], share_of_step=kmean[dom] / ms_step) if dom else None

@@ -30,6 +30,13 @@ using namespace sm100;
 #define CNB_K2_HEADS_CONST 0
 #endif
 constexpr int kHeadSrc = CNB_K2_HEADS_CONST ? 2 : 1;
+// 1: the epilogues of the 256-wide layers keep four tcgen05.ld in flight (software pipeline, see fwd_epilogue_layer).
+// Measured on the CTA-pair kernel (round 2, same-session A/B): training +-0, latent fit 3 % SLOWER (a few spills with
+// the prefetched encodings live); the TMEM latency is not what the epilogues wait for.  Off.
+#ifndef CNB_K2_DEEP_LD
+#define CNB_K2_DEEP_LD 0
+#endif
+constexpr bool kDeep = CNB_K2_DEEP_LD != 0;
 
 #ifdef CNB_TRACE
 extern "C" int cnb_debug_events_bwd(unsigned long long* out, unsigned int* counts, int reset) {
@@ -241,6 +248,39 @@ __device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const u
 template <bool HAS_MASK, bool ADD_SIGMA>
 __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_t (&a8)[8], const uint32_t* mscr,
                                                    uint64_t dsp2, const float* __restrict__ w_sigma, uint64_t pol) {
+    if constexpr (kDeep) {
+        // software pipeline: the next two tcgen05.ld (and their ReLU bit words) are issued before the current two chunks
+        // are processed; only the first wait exposes the TMEM latency
+        uint32_t ra[32], rb[32], rc[32], rd[32];
+        uint32_t m[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[c] = HAS_MASK ? umma::ld_global_hint(mscr + (size_t)c * kTileRows, pol) : 0xffffffffu;
+        umma::tmem_ld32(taddr + 0, ra);
+        umma::tmem_ld32(taddr + 32, rb);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(ra); tmem_regs_ready(rb);
+        umma::tmem_ld32(taddr + 64, rc);
+        umma::tmem_ld32(taddr + 96, rd);
+        bwd_epilogue32<0, HAS_MASK, ADD_SIGMA>(ra, a8, m[0], dsp2, w_sigma);
+        bwd_epilogue32<1, HAS_MASK, ADD_SIGMA>(rb, a8, m[1], dsp2, w_sigma);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(rc); tmem_regs_ready(rd);
+        umma::tmem_ld32(taddr + 128, ra);
+        umma::tmem_ld32(taddr + 160, rb);
+        bwd_epilogue32<2, HAS_MASK, ADD_SIGMA>(rc, a8, m[2], dsp2, w_sigma);
+        bwd_epilogue32<3, HAS_MASK, ADD_SIGMA>(rd, a8, m[3], dsp2, w_sigma);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(ra); tmem_regs_ready(rb);
+        umma::tmem_ld32(taddr + 192, rc);
+        umma::tmem_ld32(taddr + 224, rd);
+        bwd_epilogue32<4, HAS_MASK, ADD_SIGMA>(ra, a8, m[4], dsp2, w_sigma);
+        bwd_epilogue32<5, HAS_MASK, ADD_SIGMA>(rb, a8, m[5], dsp2, w_sigma);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(rc); tmem_regs_ready(rd);
+        bwd_epilogue32<6, HAS_MASK, ADD_SIGMA>(rc, a8, m[6], dsp2, w_sigma);
+        bwd_epilogue32<7, HAS_MASK, ADD_SIGMA>(rd, a8, m[7], dsp2, w_sigma);
+        return;
+    }
     auto pair = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
         uint32_t ra[32], rb[32];
@@ -582,8 +622,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
                             const uint32_t tok = bar_sync_token(1 + g, 128);
                             const float* bias = smem_fptr(sb, tok);
-                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
-                            else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                             else if (p.fuse_comp) {
                                 if (store) fwd_epilogue_layer<4, 2, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                                 else fwd_epilogue_layer<4, 2, false, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);

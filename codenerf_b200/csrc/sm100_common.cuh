@@ -223,12 +223,49 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
     if (MASK && RELU) umma::st_global_hint(mscr + (size_t)CC * kTileRows, ~sgn, acc.mask_policy);   // bit set <=> pre-activation >= +0
 }
 
-// A whole layer: NCC x 32 columns, two tcgen05.ld in flight per wait.  (Four in flight, with the registers that
-// setmaxnreg frees, measured no faster and leaves no room for the next tile's prefetched encodings.)
-template <int NCC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC>
+// Ties the registers of a tcgen05.ld result to program order after the tcgen05.wait::ld that precedes this call (an
+// empty volatile asm per register: no instruction, but nothing that uses r[] may be scheduled above it).
+__device__ __forceinline__ void tmem_regs_ready(uint32_t (&r)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(r[i]));
+}
+
+// A whole layer: NCC x 32 columns.  DEEP = false: two tcgen05.ld in flight per wait.  DEEP = true (NCC = 8): software
+// pipeline, the next two loads are issued before the current two chunks are processed, so only the first wait of a
+// layer exposes the TMEM latency (~300 cycles each; with CTA pairs the kernels' period is MMA + epilogue, so the
+// epilogue's stalls count -- in round 1, when the weight ring set the period, this measured +-0).
+template <int NCC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC, bool DEEP = false>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                    const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
+    if constexpr (DEEP && NCC == 8) {
+        uint32_t ra[32], rb[32], rc[32], rd[32];
+        umma::tmem_ld32(taddr + 0, ra);
+        umma::tmem_ld32(taddr + 32, rb);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(ra); tmem_regs_ready(rb);
+        umma::tmem_ld32(taddr + 64, rc);
+        umma::tmem_ld32(taddr + 96, rd);
+        fwd_epilogue32<0, KIND, STORE, MASK, SRC, HSRC>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<1, KIND, STORE, MASK, SRC, HSRC>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(rc); tmem_regs_ready(rd);
+        umma::tmem_ld32(taddr + 128, ra);
+        umma::tmem_ld32(taddr + 160, rb);
+        fwd_epilogue32<2, KIND, STORE, MASK, SRC, HSRC>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<3, KIND, STORE, MASK, SRC, HSRC>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(ra); tmem_regs_ready(rb);
+        umma::tmem_ld32(taddr + 192, rc);
+        umma::tmem_ld32(taddr + 224, rd);
+        fwd_epilogue32<4, KIND, STORE, MASK, SRC, HSRC>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<5, KIND, STORE, MASK, SRC, HSRC>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        umma::tmem_ld_wait();
+        tmem_regs_ready(rc); tmem_regs_ready(rd);
+        fwd_epilogue32<6, KIND, STORE, MASK, SRC, HSRC>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<7, KIND, STORE, MASK, SRC, HSRC>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        return;
+    }
     auto pair = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
         uint32_t ra[32], rb[32];
