@@ -187,7 +187,10 @@ extern "C" size_t cnb_mlp_workspace_bytes(const cnb_net_config* cfg, int64_t S, 
     if (cnb_validate_config(cfg) != CNB_OK || S <= 0 || n_codes < 1) return 0;
     if (precision == CNB_PRECISION_FP32) return cnb_fp32_workspace_bytes(cfg, S, 0, n_codes, backward, 0);
     size_t n = cnb_sm100_mlp_workspace_bytes(cfg, S, n_codes, backward);
-    if (backward && !cnb_sm100_has_backward()) {
+    // codes that change inside a 128-row tile (e.g. one code per ray, [B,1,256]): the tensor-core backward needs one
+    // code per tile and hands the call to the fp32 kernels (see cnb_mlp_backward)
+    const bool ragged_codes = backward && n_codes > 1 && ((S / n_codes) % 128) != 0;
+    if (backward && (!cnb_sm100_has_backward() || ragged_codes)) {
         const size_t m = cnb_fp32_workspace_bytes(cfg, S, 0, n_codes, backward, 0);
         if (m > n) n = m;
     }
@@ -236,6 +239,14 @@ extern "C" int cnb_mlp_backward(const cnb_net_config* cfg, const float* const* p
         return cnb_fp32_mlp_backward(cfg, params, xyz, viewdir, shape_codes, texture_codes, n_codes,
                                      n_codes > 1 ? samples_per_code : 0, S, d_sigmas, d_rgbs, d_params, d_shape_codes,
                                      d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
+    // The tensor-core backward folds the code-conditioned terms into one bias row per 128-row tile; when the codes change
+    // inside a tile (samples_per_code not a multiple of 128: per-ray codes [B,1,256] with N = 64 or 96) the gradients are
+    // computed by the fp32 kernels instead -- same mathematics, higher precision, not a throughput path (the
+    // reference's own loops always broadcast one code over a whole chunk).
+    if (n_codes > 1 && (samples_per_code % 128) != 0)
+        return cnb_fp32_mlp_backward(cfg, params, xyz, viewdir, shape_codes, texture_codes, n_codes, samples_per_code, S,
+                                     d_sigmas, d_rgbs, d_params, d_shape_codes, d_texture_codes, workspace, workspace_bytes,
+                                     (cudaStream_t)stream);
     return cnb_sm100_mlp_backward(cfg, params, packed, xyz, viewdir, shape_codes, texture_codes, n_codes,
                                   n_codes > 1 ? samples_per_code : 0, S, d_sigmas, d_rgbs, d_params, d_shape_codes,
                                   d_texture_codes, workspace, workspace_bytes, (cudaStream_t)stream);
@@ -248,7 +259,9 @@ extern "C" size_t cnb_render_workspace_bytes(const cnb_net_config* cfg, const cn
     if (precision == CNB_PRECISION_FP32)
         return cnb_fp32_workspace_bytes(cfg, rays->n_rays * rays->n_samples, rays->n_samples, rays->n_codes, backward, 1);
     size_t n = cnb_sm100_render_workspace_bytes(cfg, rays, backward);
-    if (backward && !cnb_sm100_has_backward()) {
+    const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * rays->n_samples;
+    const bool ragged_codes = backward && rays->n_codes > 1 && (rows_per_code % 128) != 0;
+    if (backward && (!cnb_sm100_has_backward() || ragged_codes)) {
         const size_t m = cnb_fp32_workspace_bytes(cfg, rays->n_rays * rays->n_samples, rays->n_samples, rays->n_codes, backward, 1);
         if (m > n) n = m;
     }
@@ -270,7 +283,8 @@ static int render_dispatch(const cnb_net_config* cfg, const float* const* params
                                d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
     if (precision != CNB_PRECISION_BF16) return CNB_E_INVALID;
     if (!packed) return CNB_E_INVALID;
-    if (mode != 0 && !cnb_sm100_has_backward())
+    const int64_t rows_per_code = (int64_t)rays->segments_per_code * rays->rays_per_segment * rays->n_samples;
+    if (mode != 0 && (!cnb_sm100_has_backward() || (rays->n_codes > 1 && (rows_per_code % 128) != 0)))   // see cnb_mlp_backward
         return cnb_fp32_render(cfg, params, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc, sq_err,
                                d_params, d_shape, d_tex, ws, ws_bytes, (cudaStream_t)stream);
     return cnb_sm100_render(cfg, params, packed, rays, mode, d_rgb, d_depth, target, loss_scale, rgb, depth, acc,

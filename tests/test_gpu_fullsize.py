@@ -140,3 +140,68 @@ def test_backward_kernel_variants_match_default(env):
     for a, b in zip(got, base):
         s = float(b.abs().max())
         assert float((a - b).abs().max()) <= 1e-4 * max(s, 1e-30)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_samples", [64, 96])
+def test_full_batch_objects_against_the_oracle(n_samples):
+    """Direct parity at BASELINE's full size: three objects taken out of the 32-object training batch (first, one whose
+    rows lie inside a sub-batch, last) are re-run on the CPU oracle (2048 rays each, ~1 s per object): image, squared
+    error and the latent-code gradients of the fused step; and the sum of the three objects' weight gradients against
+    a fused step over just those objects."""
+    import bench
+    import codenerf_b200 as cn
+    from codenerf_b200 import _lib, ops
+    from oracle import oracle as orc
+    model, flat = U.make_model("bf16")
+    c2w, pix, z, tgt, sc, tc = bench.synthetic_batch(N_OBJ, 0, n_samples)
+    dev = "cuda"
+    focal = torch.tensor([syn.SRN_FOCAL], dtype=torch.float64)
+    T = lambda a: torch.from_numpy(a).to(dev)
+    params = model.param_list(); packed = model._packed.get(model._cfg, params)
+    n_par = sum(p.numel() for p in params)
+
+    def step(idx):
+        b = cn.RayBundle(z_vals=T(z[idx]), rays_per_segment=RAYS, c2w=T(c2w[idx]), pix_begin=T(pix[idx]), focal=focal,
+                         H=syn.SRN_HW, W=syn.SRN_HW)
+        dP = torch.zeros(n_par, device=dev)
+        t_sel = np.concatenate([tgt[g * RAYS:(g + 1) * RAYS] for g in idx])
+        out = ops.render_train_step(model._cfg, params, packed, b.args(T(sc[idx]), T(tc[idx])), _lib.PRECISION_BF16,
+                                    T(t_sel), 1.0, dP, want_outputs=True)
+        return dP, out
+
+    dP_all, (rgb, depth, acc, sq, dsc, dtc) = step(list(range(N_OBJ)))
+    _no_timeouts()
+    picks = [0, 13, N_OBJ - 1]
+    dP_ref = np.zeros(n_par, np.float32)
+    for g in picks:
+        fwd = orc.render(flat, syn.SRN_HW, syn.SRN_HW, syn.SRN_FOCAL, c2w[g], z[g], sc[g:g + 1], tc[g:g + 1], True,
+                         ray_begin=int(pix[g]), ray_count=RAYS)
+        t_g = tgt[g * RAYS:(g + 1) * RAYS]
+        sl = slice(g * RAYS, (g + 1) * RAYS)
+        np.testing.assert_allclose(rgb[sl].cpu().numpy(), fwd["rgb"], atol=1e-2, rtol=0)
+        np.testing.assert_allclose(depth[sl].cpu().numpy(), fwd["depth"], atol=1e-2, rtol=0)
+        np.testing.assert_allclose(acc[sl].cpu().numpy(), fwd["acc"], atol=1e-2, rtol=0)
+        np.testing.assert_allclose(float(sq[g]), float(((fwd["rgb"] - t_g) ** 2).sum()), rtol=2e-2)
+        d_rgb = (2.0 * (fwd["rgb"] - t_g) / (3.0 * RAYS)).astype(np.float32)
+        dP_g, ds_g, dt_g = orc.render_backward(flat, fwd, z[g], sc[g:g + 1], tc[g:g + 1], d_rgb, None, True)
+        dP_ref += dP_g
+        e_s, e_t = U.rel_err(dsc[g].cpu().numpy(), ds_g[0]), U.rel_err(dtc[g].cpu().numpy(), dt_g[0])
+        print(f"N={n_samples} object {g}: d_shape rel err {e_s:.3e}, d_tex {e_t:.3e}")
+        assert e_s < 4e-2 and e_t < 4e-2, (g, e_s, e_t)
+    # weight gradients: the fused step over the three objects alone against the oracle's sum ...
+    dP_sel, out_sel = step(picks)
+    got = dP_sel.cpu().numpy()
+    o = 0
+    worst = 0.0
+    for key, shp in orc.param_shapes():
+        n = int(np.prod(shp))
+        e, c = U.rel_err(got[o:o + n], dP_ref[o:o + n]), U.cosine(got[o:o + n], dP_ref[o:o + n])
+        worst = max(worst, e)
+        # a one-element tensor (sigma.0.bias) is a signed sum with cancellation: its relative error is not damped by a max
+        assert e < (4e-2 if n > 3 else 1e-1) and c > 0.999, (key, e, c)
+        o += n
+    print(f"N={n_samples}: worst weight-gradient rel err of 3 full-size objects vs the oracle {worst:.3e}")
+    # ... and those objects' code gradients do not depend on the batch they were computed in
+    for k, g in enumerate(picks):
+        assert U.rel_err(out_sel[4][k].cpu().numpy(), dsc[g].cpu().numpy()) < 1e-3
