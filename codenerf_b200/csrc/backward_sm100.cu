@@ -84,6 +84,12 @@ struct BwdParams {
     uint32_t* mask_scratch;         // [grid][2 groups][1 + lookahead][n_layers][8][128]
     float* colsum;                  // [n_codes][n_layers][256] += column sums of dY_l
     int stash;                      // 1: stream operand tiles + dspre to HBM (training)
+    // rgb.2 weight gradient inside K2 (training): d W_rgb2 = sum_rows d_rgb (x) r1 as one small MMA per tile -- A = the
+    // rgb.2 input r1 still in the operand buffer (MN-major: its 128 columns are M), B = the tile's per-sample d_rgb (bf16
+    // hi + lo) written into the idle PE(viewdir) block (MN-major, N = 32) -- read back from TMEM into three registers per
+    // thread.  r1 is then neither stashed (32 KB per tile) nor re-read by a head kernel (0.47 ms per step).
+    int head_mma;
+    float *d_wrgb2, *d_brgb2;
     int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
     int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
     uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
@@ -395,7 +401,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         uint32_t cnt[2] = {0u, 0u};               // operands consumed so far per group (a_ready parity)
         CNB_TR_DECL(tr_wa); CNB_TR_DECL(tr_ww); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
-        auto issue = [&](int g, int n_kchunks, int n_halves, int has_dir, int ev_op) {
+        auto issue = [&](int g, int n_kchunks, int n_halves, int has_dir, int ev_op, uint32_t a_shift = 0u) {
             const uint32_t par = cnt[g] & 1u; ++cnt[g];
             if (CG == 2 && rank != 0) return;            // the partner CTA issues no MMAs
             if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], par));
@@ -403,12 +409,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             CNB_EV(lane, 0, (1 << 12) | (g << 8) | ev_op);          // operands ready, issue starts
             umma::tc_fence_after();
             if (CG == 2)
-                issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                issue_gemm_2cta(umma::smem_u32(sA0 + g * kATile) + a_shift, tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
                                 n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
             else
-                issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile), tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
+                issue_gemm<MC>(umma::smem_u32(sA0 + g * kATile) + a_shift, tmem + (uint32_t)g * 256u, sW, w_full, w_empty, n_kchunks,
                                n_halves, has_dir, stage, ph, &acc_full[g], &tr_ww);
             CNB_EV(lane, 0, (2 << 12) | (g << 8) | ev_op);          // all MMAs of the op issued
+        };
+        // rgb.2 weight gradient of one tile: D[m = r1 column][n] = sum_rows r1[row][m] * seeds[row][n], contraction over the
+        // tile's 128 rows (8 K steps of 16 rows).  Both operands are MN-major views of shared-memory images that exist
+        // anyway (the same views K3 takes of the stash).  On CTA pairs (M = 256, N = 64) each CTA supplies its own r1 as its
+        // half of M and its own seeds as its half of N, and reads only its own half of the N columns of D: the other half
+        // pairs its r1 with the partner's seeds and is ignored.
+        auto issue_head = [&](int g) {
+            const uint32_t par = cnt[g] & 1u; ++cnt[g];
+            if (CG == 2 && rank != 0) return;
+            if (CG == 2) CNB_TR(tr_wa, umma::mbar_wait_cluster(&a_ready[g], par));
+            else CNB_TR(tr_wa, umma::mbar_wait(&a_ready[g], par));
+            umma::tc_fence_after();
+            if (umma::elect_one()) {
+                const uint32_t a_base = umma::smem_u32(sA0 + g * kATile);
+                const uint64_t dA = umma::make_sdesc(a_base, kABlock, 1024, umma::SWZ_128B);              // two 64-column spans, 16 KB apart
+                const uint64_t dB = umma::make_sdesc(a_base + 4 * kABlock, kDirBlock / 2, 512, umma::SWZ_64B);
+                const uint32_t idesc = CG == 2 ? umma::make_idesc(256, 64, 1, 1) : umma::make_idesc(128, 32, 1, 1);
+                const uint32_t d = tmem + (uint32_t)g * 256u;
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    if (CG == 2) umma::mma_bf16_2cta(d, dA + (uint64_t)(ks * 128), dB + (uint64_t)(ks * 64), idesc, ks > 0 ? 1u : 0u);
+                    else umma::mma_bf16(d, dA + (uint64_t)(ks * 128), dB + (uint64_t)(ks * 64), idesc, ks > 0 ? 1u : 0u);
+                }
+                if (CG == 2) umma::mma_commit_2cta(&acc_full[g], 3); else umma::mma_commit(&acc_full[g]);
+            }
+            __syncwarp();
         };
         for (int r = 0; r < rounds; ++r)
             for (int i = 0; i < U + LA; ++i) {
@@ -416,10 +448,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     for (int op = 0; op < nl; ++op)
                         for (int g = 0; g < 2; ++g)
                             if (2 * r + g < UN) issue(g, p.layers[op].n_kchunks, p.layers[op].n_halves, p.layers[op].has_dir, op);
-                if (i >= LA)
+                if (i >= LA) {
+                    if (p.stash && p.head_mma)
+                        for (int g = 0; g < 2; ++g)
+                            if (2 * r + g < UN) issue_head(g);
                     for (int s = 1; s < ns; ++s)
                         for (int g = 0; g < 2; ++g)
-                            if (2 * r + g < UN) issue(g, p.steps[s].n_kchunks, 2, 0, nl + s - 1);
+                            if (2 * r + g < UN) issue(g, p.steps[s].n_kchunks, 2, 0, nl + s - 1, (s == 1 && p.stash && p.head_mma) ? 2u * kABlock : 0u);
+                }
             }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         CNB_TR_FLUSH(0, tr_wa); CNB_TR_FLUSH(1, tr_ww); CNB_TR_FLUSH(2, tr_tot);
@@ -436,6 +472,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
             const bool stash = p.stash && live;
             if (p.stash_wrap > 0) tile %= p.stash_wrap;
+            // with the in-kernel rgb.2 gradient step 0 writes blocks 2-3 (blocks 0-1 still hold r1 for that MMA)
+            const uint8_t* src = sA + ((phs == nl + 1 && p.stash && p.head_mma) ? 2 * kABlock : 0);
             int blocks = 0, out_layer = -1;
             uint8_t* dst = nullptr;
             if (phs == 0) { blocks = 1; dst = p.stashA + (size_t)tile * p.a_tile_bytes + p.a_slot[0]; }
@@ -451,7 +489,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
                 const uint32_t piece = (uint32_t)blocks * (kABlock / p.stash_lanes);
                 if (lane < p.stash_lanes) {
-                    umma::bulk_s2g_hint(dst + (size_t)lane * piece, sA + (size_t)lane * piece, piece, pol_stream);
+                    umma::bulk_s2g_hint(dst + (size_t)lane * piece, src + (size_t)lane * piece, piece, pol_stream);
                     if (phs == 0)
                         umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot + lane * (kDirBlock / p.stash_lanes),
                                             sA + 4 * kABlock + lane * (kDirBlock / p.stash_lanes), kDirBlock / p.stash_lanes, pol_stream);
@@ -465,7 +503,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 float acc[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-                const uint8_t* base = sA + blk * kABlock;
+                const uint8_t* base = src + blk * kABlock;
 #pragma unroll 4
                 for (int rr = 0; rr < kTileRows; ++rr) {
                     const uint4 w = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
@@ -489,7 +527,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     const int64_t tile = utile0 + i;
                     const bool live = u < UN_own && tile < tiles;
                     for (int phs = 0; phs <= nl; ++phs) {
-                        if (phs == nl && !p.stash) continue;      // the rgb.2 input is only written for the stash
+                        if (phs == nl && (!p.stash || p.head_mma)) continue;      // the rgb.2 input is only stashed for the head kernel
                         phase(tile, live, phs);
                     }
                 }
@@ -519,6 +557,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const uint64_t pol_keep = umma::l2_policy_evict_last();   // ReLU masks: written now, re-read ~50 us later
         uint32_t wp = 0;      // operand-buffer write phases so far (buf_free bookkeeping)
         uint32_t opc = 0;     // accumulator phases consumed
+        const bool head_mma = p.stash && p.head_mma;
+        float hw[3] = {0.f, 0.f, 0.f};      // d rgb.2.weight[k][row]: this thread's TMEM lane is the rgb.2 input column `row`
+        float hb[3] = {0.f, 0.f, 0.f};      // d rgb.2.bias[k], this thread's rows
         const size_t mask_set = (size_t)nl * 8 * kTileRows;      // words of one tile's ReLU masks
         uint32_t* mscr = p.mask_scratch + (size_t)(blockIdx.x * 2 + g) * (1 + LA) * mask_set + row;
         const int tg = (warp & 3) * 32 + lane;           // thread index inside the group
@@ -646,7 +687,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                                 else fwd_epilogue_layer<4, 0, false, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                             }
                         }
-                        if (store) publish(!last);
+                        if (store && !(last && head_mma)) publish(!last);      // (r1 for the in-kernel rgb.2 gradient is published with the seeds)
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | l);      // epilogue done, operand published
                         tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
                     }
@@ -702,12 +743,30 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     const float dspre = x > 20.f ? ds : ds * ex / (ex + 1.f);      // softplus backward (ATen form)
                     if (p.stash && valid) {
                         p.dspre[lrow] = dspre;
-                        if (p.fuse_comp) { p.drgb_out[lrow * 3] = dcr; p.drgb_out[lrow * 3 + 1] = dcg; p.drgb_out[lrow * 3 + 2] = dcb; }
+                        if (p.fuse_comp && !head_mma) { p.drgb_out[lrow * 3] = dcr; p.drgb_out[lrow * 3 + 1] = dcg; p.drgb_out[lrow * 3 + 2] = dcb; }
                     }
                     const uint32_t* mset = mscr + (size_t)(LA ? (ib & 1) : 0) * mask_set;
+                    if (head_mma) {
+                        // this row's d_rgb as bf16 hi + lo -> chunk 0 of its row of the (idle) PE(viewdir) block: the B operand
+                        // of the rgb.2 weight-gradient MMA; r1, its A operand, is still in blocks 0-1
+                        const float s3[3] = {valid ? dcr : 0.f, valid ? dcg : 0.f, valid ? dcb : 0.f};
+                        float hi[3], lo[3];
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            hi[k] = __bfloat162float(__float2bfloat16_rn(s3[k]));
+                            lo[k] = s3[k] - hi[k];
+                            hb[k] += s3[k];
+                        }
+                        st_shared_v4(sA + 4 * kABlock + row * 64 + ((0 ^ ((row >> 1) & 3)) << 4), umma::pack_bf16(hi[0], hi[1]),
+                                     umma::pack_bf16(hi[2], lo[0]), umma::pack_bf16(lo[1], lo[2]), 0u);
+                        umma::tc_fence_before();
+                        umma::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
+                    }
 
                     // ---- step 0: gradient of the rgb.0 pre-activation = (d_rgb . W_rgb2) * relu' ----
-                    wait_buf_free();
+                    if (!head_mma) wait_buf_free();      // (with the in-kernel head gradient: blocks 2-3, free since the rgb.0 GEMM)
                     {
                         const float* wrgb_s = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWrgb) : smem_fptr(sWrgb, order_token());
                         const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
@@ -729,9 +788,24 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                                 f2 = (mlast & (0x80000000u >> (pos + 2))) ? f2 : 0.f; f3 = (mlast & (0x80000000u >> (pos + 3))) ? f3 : 0.f;
                                 w[hh * 2 + 0] = cvt_bf16x2<false>(pk2f(f0, f1)); w[hh * 2 + 1] = cvt_bf16x2<false>(pk2f(f2, f3));
                             }
-                            if (c8 < 8) st_shared_v4_off<0>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
-                            else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                            if (head_mma) {
+                                if (c8 < 8) st_shared_v4_off<2 * kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                                else st_shared_v4_off<3 * kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                            } else {
+                                if (c8 < 8) st_shared_v4_off<0>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                                else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
+                            }
                         }
+                    }
+                    if (head_mma) {
+                        // the small MMA has had the whole of step 0 to finish: D[m = row][0..5] = sum over the tile's rows
+                        CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                        umma::tc_fence_after();
+                        uint32_t d8[8];
+                        umma::tmem_ld8(taddr + (CG == 2 ? rank * 32u : 0u), d8);
+                        umma::tmem_ld_wait();
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) hw[k] += __uint_as_float(d8[k]) + __uint_as_float(d8[k + 3]);
                     }
                     publish(ns > 1);
                     if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (5 << 12) | (g << 8) | nl);         // compositing + step 0 done
@@ -762,6 +836,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
                     }
                 }
+            }
+        }
+        if (head_mma) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                atomicAdd(p.d_wrgb2 + k * (kW / 2) + row, hw[k]);
+                const float b = warp_sum_f(hb[k]);
+                if (lane == 0) atomicAdd(p.d_brgb2 + k, b);
             }
         }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
@@ -1332,6 +1414,8 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
     bp.mask_scratch = w.masks; bp.colsum = w.colsum;
     bp.stash_wrap = cnb_option("stash_wrap", 0);
+    bp.head_mma = 0;      // set below, once the unit shape is known
+    bp.d_wrgb2 = d_params ? d_params + L.rgb2_w : nullptr; bp.d_brgb2 = d_params ? d_params + L.rgb2_b : nullptr;
     bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux
@@ -1349,6 +1433,9 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
         bp.drgb_out = drgb_buf;
         d_rgbs = drgb_buf;        // the head weight gradient reads the per-sample seeds K2 writes
     }
+    // the in-kernel rgb.2 gradient needs the tile's r1 still in the operand buffer when its backward chain starts: not with
+    // the one-tile lookahead of straddling rays (the next tile's forward chain has overwritten it) -- those use the head kernel
+    bp.head_mma = (d_params && bp.lookahead == 0 && cnb_option("head_mma", 1) != 0) ? 1 : 0;
     for (int l = 0; l <= nl; ++l) bp.a_slot[l] = sl.a_slot[l];
     for (int l = 0; l < nl; ++l) bp.d_slot[l] = sl.d_slot[l];
     bp.dir_slot = sl.dir_slot; bp.a_tile_bytes = sl.a_tile_bytes; bp.d_tile_bytes = sl.d_tile_bytes;
@@ -1452,12 +1539,15 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     k_wgrad<<<wgrid, kWgThreads, wsmem, st2>>>(wp);
     cnb_prof_end(CNB_K_WGRAD, st2);
     CNB_LAUNCH_CHECK();
-    // rgb.2 head: input r1 = the rgb.0 hidden (the sigma head is reduced inside K3)
-    const int64_t hwant = (tiles + kHeadWarps / 2 - 1) / (kHeadWarps / 2);
-    const int hgrid = (int)(hwant < 2 * sms ? hwant : 2 * sms);
-    k_head_wgrad<<<hgrid, kHeadWarps * 32, 0, st2>>>(stashA, sl.a_tile_bytes, sl.a_slot[nl], d_rgbs, S, tiles,
-                                                    d_params + L.rgb2_w, d_params + L.rgb2_b);
-    CNB_LAUNCH_CHECK();
+    // rgb.2 head: reduced inside K2 by default (head_mma); otherwise from the stashed rgb.2 input r1 = the rgb.0 hidden
+    // (the sigma head is reduced inside K3 either way)
+    if (!bp.head_mma) {
+        const int64_t hwant = (tiles + kHeadWarps / 2 - 1) / (kHeadWarps / 2);
+        const int hgrid = (int)(hwant < 2 * sms ? hwant : 2 * sms);
+        k_head_wgrad<<<hgrid, kHeadWarps * 32, 0, st2>>>(stashA, sl.a_tile_bytes, sl.a_slot[nl], d_rgbs, S, tiles,
+                                                        d_params + L.rgb2_w, d_params + L.rgb2_b);
+        CNB_LAUNCH_CHECK();
+    }
     if (piped) {
         CNB_CUDA_TRY(cudaEventRecord(pp->k3_done[buf], pp->st3));
         pp->pending[buf] = true;
