@@ -236,16 +236,14 @@ __device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const u
         }
         uint32_t w[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (HAS_MASK) {
-                float lo, hi; unpk2(v[i], lo, hi);
-                lo = (mw & (0x80000000u >> (j8 * 8 + 2 * i))) ? lo : 0.f;
-                hi = (mw & (0x80000000u >> (j8 * 8 + 2 * i + 1))) ? hi : 0.f;
-                w[i] = cvt_bf16x2<false>(pk2f(lo, hi));
-            } else {
-                w[i] = cvt_bf16x2<false>(v[i]);
-            }
+        for (int i = 0; i < 4; ++i) w[i] = cvt_bf16x2<false>(v[i]);
+#ifndef CNB_EXPERIMENT_NOMASK     // (timing experiment only, wrong gradients)
+        if (HAS_MASK) {         // columns 8 j8 + 2 i, + 1: bits of word << (2 j8 + (i >> 1)), byte pair i & 1 (relu_mask_pair)
+            const uint32_t x0 = mw << (2 * j8), x1 = mw << (2 * j8 + 1);
+            w[0] &= relu_mask_pair(x0, 0); w[1] &= relu_mask_pair(x0, 1);
+            w[2] &= relu_mask_pair(x1, 0); w[3] &= relu_mask_pair(x1, 1);
         }
+#endif
         constexpr int blk = CC >> 1;
         const int chunk = ((CC & 1) << 2) + j8;
         st_shared_v4_off<blk * kABlock>(a8[chunk], w[0], w[1], w[2], w[3]);
@@ -782,11 +780,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                                 const float4 w2 = ld_vec4<kHeadSrc>(wrgb_s + kW + col + hh * 4);
                                 uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
                                 uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
-                                float f0, f1, f2, f3; unpk2(v0, f0, f1); unpk2(v1, f2, f3);
-                                const int pos = (col & 31) + hh * 4;
-                                f0 = (mlast & (0x80000000u >> (pos + 0))) ? f0 : 0.f; f1 = (mlast & (0x80000000u >> (pos + 1))) ? f1 : 0.f;
-                                f2 = (mlast & (0x80000000u >> (pos + 2))) ? f2 : 0.f; f3 = (mlast & (0x80000000u >> (pos + 3))) ? f3 : 0.f;
-                                w[hh * 2 + 0] = cvt_bf16x2<false>(pk2f(f0, f1)); w[hh * 2 + 1] = cvt_bf16x2<false>(pk2f(f2, f3));
+                                // columns col + 4 hh .. + 3 of the chunk: word << ((col & 31) / 4 + hh), both byte pairs
+                                const uint32_t x = mlast << (((col & 31) >> 2) + hh);
+                                w[hh * 2 + 0] = cvt_bf16x2<false>(v0) & relu_mask_pair(x, 0);
+                                w[hh * 2 + 1] = cvt_bf16x2<false>(v1) & relu_mask_pair(x, 1);
                             }
                             if (head_mma) {
                                 if (c8 < 8) st_shared_v4_off<2 * kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);

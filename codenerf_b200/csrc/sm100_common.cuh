@@ -154,6 +154,18 @@ __device__ __forceinline__ uint32_t bar_sync_token(uint32_t id, uint32_t threads
     return tok;
 }
 
+// ReLU bit words (one per row and 32-column chunk): column c of the chunk is bit 8 (c & 3) + 7 - (c >> 2), i.e. byte k
+// holds columns k, k + 4, ..., k + 28 from its bit 7 down.  With that order ONE shift (x = word << j) puts the bits of the
+// four columns 4 j .. 4 j + 3 into the four byte sign positions, and a byte permute with sign replication turns two of
+// them into the 0xffff / 0x0000 halves that mask a packed bf16 pair: 1.25 instructions per column in the backward
+// epilogues instead of a bit test and a select each (the masks were ~1 ms of the 8.5 ms of K2 per step).
+__device__ __forceinline__ uint32_t relu_mask_pair(uint32_t x, int h) {      // halves mask of columns 4 j + 2 h, 4 j + 2 h + 1
+    uint32_t d;
+    if (h == 0) asm("prmt.b32 %0, %1, %1, 0x9988;" : "=r"(d) : "r"(x));
+    else asm("prmt.b32 %0, %1, %1, 0xbbaa;" : "=r"(d) : "r"(x));
+    return d;
+}
+
 // Accumulators of the narrow heads carried across a layer's epilogue as packed pairs.
 struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 
@@ -168,7 +180,9 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
                                                const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr,
                                                bool do_store = true) {
     constexpr bool RELU = (KIND != 1);
-    uint32_t sgn = 0u;
+    // ReLU bit word of the chunk (see relu_mask_pair): byte k collects the sign bits of columns k, k + 4, ..., k + 28,
+    // first column in bit 7 -- four independent funnel-shift chains
+    uint32_t sg0 = 0u, sg1 = 0u, sg2 = 0u, sg3 = 0u;
 #pragma unroll
     for (int j8 = 0; j8 < 4; ++j8) {
         constexpr int dummy = 0; (void)dummy;
@@ -185,16 +199,16 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
         v[2] = fadd2(pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]), pk2f(b1.x, b1.y));
         v[3] = fadd2(pk2(rr[j8 * 8 + 6], rr[j8 * 8 + 7]), pk2f(b1.z, b1.w));
 #endif
-        if (MASK && RELU) {     // collect the sign bits of the pre-activations (column c -> bit 31 - c%32)
-            uint32_t s8 = 0u;   // 8 bits per group: four short dependency chains instead of one 32-deep chain
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                float lo, hi; unpk2(v[i], lo, hi);
-                s8 = __funnelshift_l(__float_as_uint(lo), s8, 1);
-                s8 = __funnelshift_l(__float_as_uint(hi), s8, 1);
-            }
-            sgn = (sgn << 8) | s8;
+#ifndef CNB_EXPERIMENT_NOMASK     // (timing experiment only, wrong gradients: what the ReLU bit masks cost)
+        if (MASK && RELU) {     // columns 8 j8 + e, e = 0..7: e and e + 4 go to byte e & 3, in this order
+            float e0, e1, e2, e3, e4, e5, e6, e7;
+            unpk2(v[0], e0, e1); unpk2(v[1], e2, e3); unpk2(v[2], e4, e5); unpk2(v[3], e6, e7);
+            sg0 = __funnelshift_l(__float_as_uint(e0), sg0, 1); sg1 = __funnelshift_l(__float_as_uint(e1), sg1, 1);
+            sg2 = __funnelshift_l(__float_as_uint(e2), sg2, 1); sg3 = __funnelshift_l(__float_as_uint(e3), sg3, 1);
+            sg0 = __funnelshift_l(__float_as_uint(e4), sg0, 1); sg1 = __funnelshift_l(__float_as_uint(e5), sg1, 1);
+            sg2 = __funnelshift_l(__float_as_uint(e6), sg2, 1); sg3 = __funnelshift_l(__float_as_uint(e7), sg3, 1);
         }
+#endif
         if (KIND == 1) {        // sigma head on the fp32 feature (reference src/model.py:45)
             const float4 w0 = ld_vec4<HSRC>(w_sigma + col);
             const float4 w1 = ld_vec4<HSRC>(w_sigma + col + 4);
@@ -220,7 +234,10 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
                                             cvt_bf16x2<RELU>(v[2]), cvt_bf16x2<RELU>(v[3]));
         }
     }
-    if (MASK && RELU) umma::st_global_hint(mscr + (size_t)CC * kTileRows, ~sgn, acc.mask_policy);   // bit set <=> pre-activation >= +0
+#ifndef CNB_EXPERIMENT_NOMASK
+    if (MASK && RELU)       // bit set <=> pre-activation >= +0
+        umma::st_global_hint(mscr + (size_t)CC * kTileRows, ~(sg0 | (sg1 << 8) | (sg2 << 16) | (sg3 << 24)), acc.mask_policy);
+#endif
 }
 
 // Ties the registers of a tcgen05.ld result to program order after the tcgen05.wait::ld that precedes this call (an
