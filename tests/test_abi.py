@@ -46,6 +46,26 @@ def test_host_only_entry_points():
     assert L.cnb_packed_weights_bytes(ctypes.byref(cfg)) > 0
 
 
+def test_options_registry():
+    """cnb_set_option / cnb_get_option / cnb_clear_option: explicit value > CNB_<NAME> environment variable > default."""
+    from codenerf_b200 import _lib
+    L = _lib.load()
+    old = os.environ.pop("CNB_SUB_TILES", None)
+    try:
+        assert _lib.get_option("sub_tiles", 8192) == 8192
+        os.environ["CNB_SUB_TILES"] = "4096"
+        assert _lib.get_option("sub_tiles", 8192) == 4096
+        _lib.set_option("sub_tiles", 16384)
+        assert _lib.get_option("sub_tiles", 8192) == 16384
+        _lib.clear_option("sub_tiles")
+        assert _lib.get_option("sub_tiles", 8192) == 4096
+        assert L.cnb_set_option(b"no_such_option", 1) == -1
+    finally:
+        os.environ.pop("CNB_SUB_TILES", None)
+        if old is not None:
+            os.environ["CNB_SUB_TILES"] = old
+
+
 def test_state_dict_matches_reference_layout():
     """Keys / shapes of reference src/model.py:20-34."""
     import codenerf_b200 as cn
