@@ -91,6 +91,7 @@ struct BwdParams {
     int head_mma;
     float *d_wrgb2, *d_brgb2;
     int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
+    int stash_copy;                 // 1: the auxiliary warp copies the image itself (ld.shared + st.global), off the TMA queue
     int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
     uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
     uint8_t *stashA, *stashD;
@@ -482,7 +483,29 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 blocks = B.out_blocks; out_layer = B.out_layer;
                 dst = p.stashD + (size_t)tile * p.d_tile_bytes + p.d_slot[B.out_layer];
             }
-            if (stash) {
+            if (stash && p.stash_copy) {
+                // EXPERIMENT (option stash_copy, off): the warp copies the image itself, 512 coalesced bytes per instruction, 8
+                // loads in flight.  Idea: bulk stores share the SM's TMA queue with the weight refills (in training the MMA warp
+                // waits 3.5x longer for weights than in the latent fit), plain stores do not.  Measured: K2 9.9 vs 8.6 ms --
+                // one warp cannot move 64 KB per tile-op through the LSU fast enough.
+                const uint4* s4 = reinterpret_cast<const uint4*>(src) + lane;
+                uint4* d4 = reinterpret_cast<uint4*>(dst) + lane;
+                const int n512 = blocks * (kABlock / 512);
+                for (int i = 0; i < n512; i += 8) {
+                    uint4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = ld_shared_v4(reinterpret_cast<const uint8_t*>(s4 + (size_t)(i + u) * 32));
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) umma::st_global_v4_hint(d4 + (size_t)(i + u) * 32, v[u], pol_stream);
+                }
+                if (phs == 0) {
+                    const uint4* sd = reinterpret_cast<const uint4*>(sA + 4 * kABlock) + lane;
+                    uint4* dd = reinterpret_cast<uint4*>(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot) + lane;
+#pragma unroll
+                    for (int u = 0; u < kDirBlock / 512; ++u)
+                        umma::st_global_v4_hint(dd + (size_t)u * 32, ld_shared_v4(reinterpret_cast<const uint8_t*>(sd + (size_t)u * 32)), pol_stream);
+                }
+            } else if (stash) {
                 // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
                 // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
                 const uint32_t piece = (uint32_t)blocks * (kABlock / p.stash_lanes);
@@ -512,7 +535,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
             }
-            if (stash) umma::bulk_wait_read_all();
+            if (stash && !p.stash_copy) umma::bulk_wait_read_all();
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&buf_free[g]);
         };
@@ -536,7 +559,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 }
             }
         }
-        if (p.stash) umma::bulk_wait_all();
+        if (p.stash && !p.stash_copy) umma::bulk_wait_all();
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
         if (g == 0) { CNB_TR_FLUSH(3, tr_wx); CNB_TR_FLUSH(4, tr_tot); }
     }
@@ -1414,6 +1437,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.head_mma = 0;      // set below, once the unit shape is known
     bp.d_wrgb2 = d_params ? d_params + L.rgb2_w : nullptr; bp.d_brgb2 = d_params ? d_params + L.rgb2_b : nullptr;
     bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise
+    bp.stash_copy = cnb_option("stash_copy", 0) != 0 ? 1 : 0;      // measured slower (K2 9.9 vs 8.6 ms): one warp's LSU rate
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux
     // warps of K2 do it, and only for the folded layers (the latent-code gradients need nothing else)

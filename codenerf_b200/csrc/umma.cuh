@@ -106,6 +106,9 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
 __device__ __forceinline__ void st_global_hint(uint32_t* ptr, uint32_t v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(ptr), "r"(v), "l"(pol) : "memory");
 }
+__device__ __forceinline__ void st_global_v4_hint(void* ptr, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_global_hint(const uint32_t* ptr, uint64_t pol) {
     uint32_t v; asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol) : "memory"); return v;
 }
