@@ -42,6 +42,7 @@ Opt g_opts[] = {
     {"k3_sms", false, 0},         // SMs left to K3 when overlapped
     {"k3_items_per_sm_x10", false, 0},
     {"head_mma", false, 0},       // 0: rgb.2 weight gradient by the separate head kernel from the stash (default 1: inside K2)
+    {"keep_weights", false, 0},   // 0: no L2 evict_last policy on the weight loads of the training kernel (default 1)
     {"stash_copy", false, 0},     // 1: the auxiliary warp copies the stash with ld.shared / st.global instead of TMA bulk stores (slower)
     {"stash_lanes", false, 0},    // bulk stores per stashed operand image (32 = 2 KB pieces; 1, 2, 4, 8, 16)
     {"stash_wrap", false, 0},     // timing experiment: stash tile t in slot t % value (stays in L2; gradients are WRONG)

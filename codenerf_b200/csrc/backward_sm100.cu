@@ -91,6 +91,7 @@ struct BwdParams {
     int head_mma;
     float *d_wrgb2, *d_brgb2;
     int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
+    int keep_weights;               // 1: weight loads carry an L2 evict_last policy while the stash streams through L2
     int stash_copy;                 // 1: the auxiliary warp copies the image itself (ld.shared + st.global), off the TMA queue
     int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
     uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     if (warp == 0) {
         // ===== weight producer =====
         int stage = 0; uint32_t ph = 0;
-        const uint64_t pol_w = p.stash ? umma::l2_policy_evict_last() : 0ull;   // the stash stream must not evict the weights
+        const uint64_t pol_w = (p.stash && p.keep_weights) ? umma::l2_policy_evict_last() : 0ull;   // the stash stream must not evict the weights
         for (int r = 0; r < rounds; ++r)
             for (int i = 0; i < U + LA; ++i) {
                 if (i < U)
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             if (2 * r + g >= UN) continue;
                             const FwdLayer& L = p.layers[op];
                             const int n_dir = L.has_dir ? L.n_halves : 0;
-                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
+                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph, pol_w);
                             else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                         }
                 if (i >= LA)
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         for (int g = 0; g < 2; ++g) {
                             if (2 * r + g >= UN) continue;
                             const BwdStep& B = p.steps[s];
-                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph);
+                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph, pol_w);
                             else produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                         }
             }
@@ -1437,6 +1438,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.head_mma = 0;      // set below, once the unit shape is known
     bp.d_wrgb2 = d_params ? d_params + L.rgb2_w : nullptr; bp.d_brgb2 = d_params ? d_params + L.rgb2_b : nullptr;
     bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise
+    bp.keep_weights = cnb_option("keep_weights", 1) != 0 ? 1 : 0;
     bp.stash_copy = cnb_option("stash_copy", 0) != 0 ? 1 : 0;      // measured slower (K2 9.9 vs 8.6 ms): one warp's LSU rate
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux

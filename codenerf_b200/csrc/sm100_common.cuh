@@ -443,7 +443,7 @@ struct alignas(64) WeightMaps { CUtensorMap m16, m8; };
 // Every load completes on the LEADER's barrier; the leader arms it with the bytes of both CTAs.
 __device__ __forceinline__ void produce_stages_2cta(const WeightMaps* maps, uint32_t w_off, int n_kchunks, int n_halves,
                                                     int has_dir, uint32_t rank, uint8_t* sW, uint64_t* w_full,
-                                                    uint64_t* w_empty, int& stage, uint32_t& ph) {
+                                                    uint64_t* w_empty, int& stage, uint32_t& ph, uint64_t l2_policy = 0ull) {
     const int n = n_kchunks + (has_dir ? 1 : 0);
     const uint32_t full0 = umma::mapa(umma::smem_u32(&w_full[0]), 0);
     for (int c = 0; c < n; ++c) {
@@ -454,8 +454,12 @@ __device__ __forceinline__ void produce_stages_2cta(const WeightMaps* maps, uint
             const uint32_t off = dir ? w_off + (uint32_t)(n_kchunks * n_halves + rank) * kSlot
                                      : (n_halves == 2 ? w_off + (uint32_t)(c * 2 + rank) * kSlot : w_off + (uint32_t)c * kSlot + rank * (kSlot / 2));
             if (rank == 0) umma::mbar_arrive_expect_tx(&w_full[stage], small ? kSlot : 2 * kSlot);
-            umma::tma_load_2d_pair(sW + stage * kSlot, small ? (const void*)&maps->m8 : (const void*)&maps->m16, 0, (int)(off >> 7),
-                                   full0 + stage * 8);
+            if (l2_policy)
+                umma::tma_load_2d_pair_hint(sW + stage * kSlot, small ? (const void*)&maps->m8 : (const void*)&maps->m16, 0, (int)(off >> 7),
+                                            full0 + stage * 8, l2_policy);
+            else
+                umma::tma_load_2d_pair(sW + stage * kSlot, small ? (const void*)&maps->m8 : (const void*)&maps->m16, 0, (int)(off >> 7),
+                                       full0 + stage * 8);
         }
         __syncwarp();
         if (++stage == kNumStages) { stage = 0; ph ^= 1; }

@@ -262,6 +262,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// ... with an L2 eviction-priority policy (the weights must stay resident while the stash streams through L2)
+__device__ __forceinline__ void tma_load_2d_pair_hint(void* smem_dst, const void* tmap, int c0, int c1, uint32_t leader_bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1), "l"(pol) : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32.
 //   bits [4,6) D format (1 = f32), [7,10) A format (1 = bf16), [10,13) B format (1 = bf16),
