@@ -93,6 +93,7 @@ struct BwdParams {
     int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
     int keep_weights;               // 1: weight loads carry an L2 evict_last policy while the stash streams through L2
     int stash_copy;                 // 1: the auxiliary warp copies the image itself (ld.shared + st.global), off the TMA queue
+    int experiment;                 // timing experiments (option experiment, WRONG results): bit 0 no stash stores, bit 1 no weight fills for group 1
     int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
     uint32_t colsum_layers;         // bit l: the aux warps reduce column sums of dY_l (training: none, K3 does it)
     uint8_t *stashA, *stashD;
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             if (2 * r + g >= UN) continue;
                             const FwdLayer& L = p.layers[op];
                             const int n_dir = L.has_dir ? L.n_halves : 0;
-                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph, pol_w);
+                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph, pol_w, g == 1 && (p.experiment & 2));
                             else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                         }
                 if (i >= LA)
@@ -391,7 +392,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         for (int g = 0; g < 2; ++g) {
                             if (2 * r + g >= UN) continue;
                             const BwdStep& B = p.steps[s];
-                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph, pol_w);
+                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph, pol_w, g == 1 && (p.experiment & 2));
                             else produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                         }
             }
@@ -506,7 +507,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     for (int u = 0; u < kDirBlock / 512; ++u)
                         umma::st_global_v4_hint(dd + (size_t)u * 32, ld_shared_v4(reinterpret_cast<const uint8_t*>(sd + (size_t)u * 32)), pol_stream);
                 }
-            } else if (stash) {
+            } else if (stash && !(p.experiment & 1)) {
                 // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
                 // SM's copy engine slip in between (one 64 KB store ahead of a refill stalls the MMA ring)
                 const uint32_t piece = (uint32_t)blocks * (kABlock / p.stash_lanes);
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) atomicAdd(out + i, acc[i]);
             }
-            if (stash && !p.stash_copy) umma::bulk_wait_read_all();
+            if (stash && !p.stash_copy && !(p.experiment & 5)) umma::bulk_wait_read_all();      // (bit 2: release the buffer without waiting)
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(&buf_free[g]);
         };
@@ -1435,6 +1436,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.d_sigmas = d_sigmas; bp.d_rgbs = d_rgbs;
     bp.mask_scratch = w.masks; bp.colsum = w.colsum;
     bp.stash_wrap = cnb_option("stash_wrap", 0);
+    bp.experiment = (int)cnb_option("experiment", 0);
     bp.head_mma = 0;      // set below, once the unit shape is known
     bp.d_wrgb2 = d_params ? d_params + L.rgb2_w : nullptr; bp.d_brgb2 = d_params ? d_params + L.rgb2_b : nullptr;
     bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise

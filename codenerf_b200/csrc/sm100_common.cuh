@@ -21,6 +21,9 @@ constexpr int kABlock = 16384;          // activation K-block [128 rows x 64] bf
 constexpr int kDirBlock = 8192;         // PE(viewdir) block [128 rows x 32] bf16, 64-B swizzle
 constexpr int kATile = 4 * kABlock + kDirBlock;
 constexpr int kThreads = 384;           // warpgroup 0: producer, MMA issuer, 2 auxiliary warps; warps 4-7 group X, 8-11 group Y
+#ifndef CNB_EPI_PREFETCH
+#define CNB_EPI_PREFETCH 1      // epilogues load the next column group's bias / head rows before storing the current group
+#endif
 constexpr int kRegsAux = 64;            // setmaxnreg budgets: the pipeline warps give registers to the epilogue warps,
 constexpr int kRegsCompute = 216;       // which keep four 32-column TMEM loads in flight (384*168 >= 128*64 + 256*216)
 constexpr int kMaxLayers = 2 * CNB_MAX_BLOCKS + 4;
@@ -174,12 +177,22 @@ struct HeadAcc { uint64_t sig2, r2, g2, b2; uint64_t mask_policy; };
 // the next operand, [ReLU sign bits for the backward].   KIND: 0 hidden, 1 encoding_shape
 // (+ sigma head, no ReLU), 2 rgb.0 (+ rgb head).   a8[c] = shared address of 16-byte chunk c of
 // this row inside K-block 0.
-template <int CC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC>
+template <int CC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC, bool PRE_IN = false, bool PRE_OUT = false>
 __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const float* __restrict__ bias,
                                                const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
                                                const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr,
-                                               bool do_store = true) {
+                                               bool do_store = true, float4* pre = nullptr) {
     constexpr bool RELU = (KIND != 1);
+#if CNB_EPI_PREFETCH
+    // The bias row (and head weights) of column group j8 + 1 are loaded BEFORE group j8 is stored: ptxas cannot move a
+    // ld.shared above an earlier st.shared (possible alias), so loads placed next to their use sat two instructions
+    // ahead of it and every group paid the ~35-cycle shared-memory latency (ncu source view: 4 x 38 of a chunk's ~410
+    // cycles).
+    // PRE_IN / PRE_OUT: the first group of a chunk is loaded by the previous chunk (pre[0..1]).
+    float4 nb0, nb1;
+    if (PRE_IN) { nb0 = pre[0]; nb1 = pre[1]; }
+    else { nb0 = ld_vec4<SRC>(bias + CC * 32); nb1 = ld_vec4<SRC>(bias + CC * 32 + 4); }
+#endif
     // ReLU bit word of the chunk (see relu_mask_pair): byte k collects the sign bits of columns k, k + 4, ..., k + 28,
     // first column in bit 7 -- four independent funnel-shift chains
     uint32_t sg0 = 0u, sg1 = 0u, sg2 = 0u, sg3 = 0u;
@@ -192,8 +205,14 @@ __device__ __forceinline__ void fwd_epilogue32(const uint32_t (&rr)[32], const f
         v[0] = pk2(rr[j8 * 8 + 0], rr[j8 * 8 + 1]); v[1] = pk2(rr[j8 * 8 + 2], rr[j8 * 8 + 3]);
         v[2] = pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]); v[3] = pk2(rr[j8 * 8 + 6], rr[j8 * 8 + 7]);
 #else
+#if CNB_EPI_PREFETCH
+        const float4 b0 = nb0, b1 = nb1;
+        if (j8 < 3) { nb0 = ld_vec4<SRC>(bias + col + 8); nb1 = ld_vec4<SRC>(bias + col + 12); }
+        else if (PRE_OUT) { pre[0] = ld_vec4<SRC>(bias + col + 8); pre[1] = ld_vec4<SRC>(bias + col + 12); }
+#else
         const float4 b0 = ld_vec4<SRC>(bias + col);
         const float4 b1 = ld_vec4<SRC>(bias + col + 4);
+#endif
         v[0] = fadd2(pk2(rr[j8 * 8 + 0], rr[j8 * 8 + 1]), pk2f(b0.x, b0.y));
         v[1] = fadd2(pk2(rr[j8 * 8 + 2], rr[j8 * 8 + 3]), pk2f(b0.z, b0.w));
         v[2] = fadd2(pk2(rr[j8 * 8 + 4], rr[j8 * 8 + 5]), pk2f(b1.x, b1.y));
@@ -283,14 +302,20 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         fwd_epilogue32<7, KIND, STORE, MASK, SRC, HSRC>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
         return;
     }
+#if CNB_EPI_PREFETCH
+    float4 pre[2] = {ld_vec4<SRC>(bias), ld_vec4<SRC>(bias + 4)};
+#else
+    float4* pre = nullptr;
+#endif
     auto pair = [&](auto cc_tag) {
         constexpr int CC = decltype(cc_tag)::value;
+        constexpr bool P = CNB_EPI_PREFETCH != 0;
         uint32_t ra[32], rb[32];
         umma::tmem_ld32(taddr + CC * 32, ra);
         umma::tmem_ld32(taddr + CC * 32 + 32, rb);
         umma::tmem_ld_wait();
-        fwd_epilogue32<CC, KIND, STORE, MASK, SRC, HSRC>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SRC, HSRC>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        fwd_epilogue32<CC, KIND, STORE, MASK, SRC, HSRC, P, P>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
+        fwd_epilogue32<CC + 1, KIND, STORE, MASK, SRC, HSRC, P, P && (CC + 2 < NCC)>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -443,12 +468,15 @@ struct alignas(64) WeightMaps { CUtensorMap m16, m8; };
 // Every load completes on the LEADER's barrier; the leader arms it with the bytes of both CTAs.
 __device__ __forceinline__ void produce_stages_2cta(const WeightMaps* maps, uint32_t w_off, int n_kchunks, int n_halves,
                                                     int has_dir, uint32_t rank, uint8_t* sW, uint64_t* w_full,
-                                                    uint64_t* w_empty, int& stage, uint32_t& ph, uint64_t l2_policy = 0ull) {
+                                                    uint64_t* w_empty, int& stage, uint32_t& ph, uint64_t l2_policy = 0ull,
+                                                    bool skip_fill = false) {
     const int n = n_kchunks + (has_dir ? 1 : 0);
     const uint32_t full0 = umma::mapa(umma::smem_u32(&w_full[0]), 0);
     for (int c = 0; c < n; ++c) {
         umma::mbar_wait(&w_empty[stage], ph ^ 1);
-        if (umma::elect_one()) {
+        if (skip_fill) {        // timing experiment (option experiment & 2): the slot keeps whatever it holds
+            if (rank == 0 && umma::elect_one()) umma::mbar_arrive(&w_full[stage]);
+        } else if (umma::elect_one()) {
             const bool dir = c >= n_kchunks;
             const bool small = dir || n_halves == 1;
             const uint32_t off = dir ? w_off + (uint32_t)(n_kchunks * n_halves + rank) * kSlot

@@ -30,15 +30,28 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// CNB_MBAR_HINT_NS > 0: suspend-time hint of the potentially blocking try_wait (the thread still resumes as soon as the
+// phase completes; a longer limit only means fewer wake-ups of a waiting warp, i.e. fewer spin-loop instructions).
+#ifndef CNB_MBAR_HINT_NS
+#define CNB_MBAR_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
+#if CNB_MBAR_HINT_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "n"(CNB_MBAR_HINT_NS)
+        : "memory");
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
         "selp.b32 %0, 1, 0, P;\n\t}"
         : "=r"(ok)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded spin: a protocol bug must not hang the GPU box, and must not be silent either.  A wait that lasts longer
@@ -200,9 +213,15 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred P;\n\t"
+#if CNB_MBAR_HINT_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "n"(CNB_MBAR_HINT_NS) : "memory");
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"      // default acquire.cta: `.acquire.cluster` costs a CCTL.IVALL per wait
         "selp.b32 %0, 1, 0, P;\n\t}"
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
     return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
