@@ -123,6 +123,9 @@ __device__ __forceinline__ uint4 ld_shared_v4(const uint8_t* p) {
                  : "r"(umma::smem_u32(p)) : "memory");
     return v;
 }
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t d; asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
 
@@ -465,7 +468,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const int g = warp - 2;
         const uint8_t* sA = sA0 + g * kATile;
         uint32_t ap = 0;
-        const uint64_t pol_stream = umma::l2_policy_evict_first();   // the stash is written once and read by a later kernel
+        const uint64_t pol_stream = (p.experiment & 8) ? umma::l2_policy_evict_normal() : (p.experiment & 16) ? umma::l2_policy_evict_last()
+                                                                                                   : umma::l2_policy_evict_first();   // the stash is written once and read by a later kernel
         CNB_TR_DECL(tr_wx); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
         // one operand-buffer phase: wait for the write, stash it and / or reduce its column sums, release the buffer
@@ -527,11 +531,21 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 8; ++i) acc[i] = 0.f;
                 const uint8_t* base = src + blk * kABlock;
-#pragma unroll 4
-                for (int rr = 0; rr < kTileRows; ++rr) {
-                    const uint4 w = ld_shared_v4(base + rr * 128 + ((chunk ^ (rr & 7)) << 4));
-                    acc[0] += bf_lo(w.x); acc[1] += bf_hi(w.x); acc[2] += bf_lo(w.y); acc[3] += bf_hi(w.y);
-                    acc[4] += bf_lo(w.z); acc[5] += bf_hi(w.z); acc[6] += bf_lo(w.w); acc[7] += bf_hi(w.w);
+                // four rows are summed as packed bf16 pairs first (two roundings of the size the operands already carry),
+                // then widened: 7 instead of 17 instructions per row -- this warp's column sums were what the epilogue of
+                // the next step waited for in the latent fit (buf_free)
+#pragma unroll 2
+                for (int rr = 0; rr < kTileRows; rr += 4) {
+                    const uint4 w0 = ld_shared_v4(base + (rr + 0) * 128 + ((chunk ^ ((rr + 0) & 7)) << 4));
+                    const uint4 w1 = ld_shared_v4(base + (rr + 1) * 128 + ((chunk ^ ((rr + 1) & 7)) << 4));
+                    const uint4 w2 = ld_shared_v4(base + (rr + 2) * 128 + ((chunk ^ ((rr + 2) & 7)) << 4));
+                    const uint4 w3 = ld_shared_v4(base + (rr + 3) * 128 + ((chunk ^ ((rr + 3) & 7)) << 4));
+                    const uint32_t sx = add_bf16x2(add_bf16x2(w0.x, w1.x), add_bf16x2(w2.x, w3.x));
+                    const uint32_t sy = add_bf16x2(add_bf16x2(w0.y, w1.y), add_bf16x2(w2.y, w3.y));
+                    const uint32_t sz = add_bf16x2(add_bf16x2(w0.z, w1.z), add_bf16x2(w2.z, w3.z));
+                    const uint32_t sw = add_bf16x2(add_bf16x2(w0.w, w1.w), add_bf16x2(w2.w, w3.w));
+                    acc[0] += bf_lo(sx); acc[1] += bf_hi(sx); acc[2] += bf_lo(sy); acc[3] += bf_hi(sy);
+                    acc[4] += bf_lo(sz); acc[5] += bf_hi(sz); acc[6] += bf_lo(sw); acc[7] += bf_hi(sw);
                 }
                 float* out = p.colsum + ((size_t)code * nl + out_layer) * kW + blk * 64 + chunk * 8;
 #pragma unroll
