@@ -92,6 +92,8 @@ struct BwdParams {
     float *d_wrgb2, *d_brgb2;
     int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
     int keep_weights;               // 1: weight loads carry an L2 evict_last policy while the stash streams through L2
+    int stash_early;                // 1: every 64-column block of an operand image is handed to the auxiliary warp's bulk store as soon as
+                                    // the epilogue has written it (4 signals per image instead of 1): the store drains during the epilogue
     int stash_copy;                 // 1: the auxiliary warp copies the image itself (ld.shared + st.global), off the TMA queue
     int experiment;                 // timing experiments (option experiment, WRONG results): bit 0 no stash stores, bit 1 no weight fills for group 1
     int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
@@ -255,9 +257,9 @@ __device__ __forceinline__ void bwd_epilogue32(const uint32_t (&rr)[32], const u
         st_shared_v4_off<blk * kABlock>(a8[chunk], w[0], w[1], w[2], w[3]);
     }
 }
-template <bool HAS_MASK, bool ADD_SIGMA>
+template <bool HAS_MASK, bool ADD_SIGMA, class Hook>
 __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_t (&a8)[8], const uint32_t* mscr,
-                                                   uint64_t dsp2, const float* __restrict__ w_sigma, uint64_t pol) {
+                                                   uint64_t dsp2, const float* __restrict__ w_sigma, uint64_t pol, Hook hook) {
     if constexpr (kDeep) {
         // software pipeline: the next two tcgen05.ld (and their ReLU bit words) are issued before the current two chunks
         // are processed; only the first wait exposes the TMEM latency
@@ -273,22 +275,26 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
         umma::tmem_ld32(taddr + 96, rd);
         bwd_epilogue32<0, HAS_MASK, ADD_SIGMA>(ra, a8, m[0], dsp2, w_sigma);
         bwd_epilogue32<1, HAS_MASK, ADD_SIGMA>(rb, a8, m[1], dsp2, w_sigma);
+        hook(0);
         umma::tmem_ld_wait();
         tmem_regs_ready(rc); tmem_regs_ready(rd);
         umma::tmem_ld32(taddr + 128, ra);
         umma::tmem_ld32(taddr + 160, rb);
         bwd_epilogue32<2, HAS_MASK, ADD_SIGMA>(rc, a8, m[2], dsp2, w_sigma);
         bwd_epilogue32<3, HAS_MASK, ADD_SIGMA>(rd, a8, m[3], dsp2, w_sigma);
+        hook(1);
         umma::tmem_ld_wait();
         tmem_regs_ready(ra); tmem_regs_ready(rb);
         umma::tmem_ld32(taddr + 192, rc);
         umma::tmem_ld32(taddr + 224, rd);
         bwd_epilogue32<4, HAS_MASK, ADD_SIGMA>(ra, a8, m[4], dsp2, w_sigma);
         bwd_epilogue32<5, HAS_MASK, ADD_SIGMA>(rb, a8, m[5], dsp2, w_sigma);
+        hook(2);
         umma::tmem_ld_wait();
         tmem_regs_ready(rc); tmem_regs_ready(rd);
         bwd_epilogue32<6, HAS_MASK, ADD_SIGMA>(rc, a8, m[6], dsp2, w_sigma);
         bwd_epilogue32<7, HAS_MASK, ADD_SIGMA>(rd, a8, m[7], dsp2, w_sigma);
+        hook(3);
         return;
     }
     auto pair = [&](auto cc_tag) {
@@ -301,6 +307,7 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
         umma::tmem_ld_wait();
         bwd_epilogue32<CC, HAS_MASK, ADD_SIGMA>(ra, a8, m0, dsp2, w_sigma);
         bwd_epilogue32<CC + 1, HAS_MASK, ADD_SIGMA>(rb, a8, m1, dsp2, w_sigma);
+        hook(CC >> 1);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -334,7 +341,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
     uint64_t* acc_full = a_ready + 2;            // [2] accumulator complete
     uint64_t* aux_ready = acc_full + 2;          // [2] a tile operand was (re)written (every phase)
     uint64_t* buf_free = aux_ready + 2;          // [2] aux warp finished reading the operand buffer
-    uint32_t* tmem_slot = (uint32_t*)(buf_free + 2);
+    uint64_t* aux_blk = buf_free + 2;            // [2][3] (stash_early) block 1..3 of the operand image was written (block 0: aux_ready)
+    uint32_t* tmem_slot = (uint32_t*)(aux_blk + 6);
     float4* sRing = (float4*)(tmem_slot + 4);      // [2 groups][256] per-sample (sigma, r, g, b), then seeds: two tiles per group
     float* sBias = (float*)(sRing + 4 * kTileRows);  // [2 groups][2 buffers][256] per-code (folded) bias row of the layer being drained
     float* sWsig = sBias + 4 * kW;                  // (CNB_K2_HEADS_CONST == 0) [256] sigma-head weights, [3][128] rgb.2 weights
@@ -358,6 +366,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         for (int g = 0; g < 2; ++g) {
             umma::mbar_init(&a_ready[g], 4 * CG); umma::mbar_init(&acc_full[g], 1);
             umma::mbar_init(&aux_ready[g], 4); umma::mbar_init(&buf_free[g], 1);
+            for (int b = 0; b < 3; ++b) umma::mbar_init(&aux_blk[g * 3 + b], 4);
         }
         umma::fence_mbar_init();
     }
@@ -473,6 +482,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         CNB_TR_DECL(tr_wx); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
         // one operand-buffer phase: wait for the write, stash it and / or reduce its column sums, release the buffer
+        const bool early = p.stash && p.stash_early && !p.stash_copy;
+        uint32_t apb[3] = {0u, 0u, 0u};       // phases consumed of aux_blk[g][0..2]
         auto phase = [&](int64_t tile, bool live, int phs) {
             CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
             const bool stash = p.stash && live;
@@ -510,6 +521,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                     for (int u = 0; u < kDirBlock / 512; ++u)
                         umma::st_global_v4_hint(dd + (size_t)u * 32, ld_shared_v4(reinterpret_cast<const uint8_t*>(sd + (size_t)u * 32)), pol_stream);
+                }
+            } else if (early) {
+                // block by block, as the epilogue signals them (block 0 arrived with aux_ready): the image drains while the
+                // rest of it is still being written, so the buffer is free again by the time the next epilogue needs it
+                for (int b = 0; b < blocks; ++b) {
+                    if (b > 0) { CNB_TR(tr_wx, umma::mbar_wait(&aux_blk[g * 3 + b - 1], apb[b - 1] & 1u)); ++apb[b - 1]; }
+                    if (stash && !(p.experiment & 1) && lane == 0) {
+                        umma::bulk_s2g_hint(dst + (size_t)b * kABlock, src + (size_t)b * kABlock, kABlock, pol_stream);
+                        if (phs == 0) umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
+                        umma::bulk_commit();
+                    }
+                    __syncwarp();
                 }
             } else if (stash && !(p.experiment & 1)) {
                 // every lane stores 1/32 of the image: short bulk stores let the weight loads that share this
@@ -608,13 +631,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         CNB_TR_DECL(tr_epi_b); CNB_TR_DECL(tr_enc); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
         auto wait_buf_free = [&]() { if (wp > 0) CNB_TR(tr_wbuf, umma::mbar_wait(&buf_free[g], (wp - 1) & 1u)); };
+        const bool early = p.stash && p.stash_early && !p.stash_copy;
+        // (stash_early) block b of the operand image being written is complete: hand it to the auxiliary warp
+        auto block_done = [&](int b) {
+            umma::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) umma::mbar_arrive(b == 0 ? &aux_ready[g] : &aux_blk[g * 3 + b - 1]);
+        };
+        auto hook_on = [&](int b) { if (early) block_done(b); };
+        auto hook_last = [&](int b) { if (early && !head_mma) block_done(b); };      // rgb.0's output is only stashed for the head kernel
         auto publish = [&](bool to_mma) {
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
                 if (to_mma) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
-                umma::mbar_arrive(&aux_ready[g]);
+                if (!early) umma::mbar_arrive(&aux_ready[g]);
             }
             ++wp;
         };
@@ -669,6 +701,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     wait_buf_free();
                     pe_store_xyz(pe.x, sA, row);
                     pe_store_dir(pe.d, sA + 4 * kABlock, row);
+                    hook_on(0);
                     publish(true);
                     if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (6 << 12) | (g << 8));               // encodings stored: tile starts
                     tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
@@ -700,27 +733,27 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             if (2 * tg < L.n_halves * 128) *reinterpret_cast<float2*>(sb + 2 * tg) = bias2;
                             const uint32_t tok = bar_sync_token(1 + g, 128);
                             const float* bias = smem_fptr(sb, tok);
-                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
-                            else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on);
+                            else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on);
                             else if (p.fuse_comp) {
-                                if (store) fwd_epilogue_layer<4, 2, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                if (store) fwd_epilogue_layer<4, 2, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_last);
                                 else fwd_epilogue_layer<4, 2, false, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                             }
-                            else if (store) fwd_epilogue_layer<4, 0, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                            else if (store) fwd_epilogue_layer<4, 0, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_last);
                             else fwd_epilogue_layer<4, 0, false, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                         } else {
                             // fixed constant-memory slots (crow_slot): immediate addresses, uniform loads
-                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 1 * kW), a8, wsig_c, wrgb_c, hacc, ml);
+                            if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 1 * kW), a8, wsig_c, wrgb_c, hacc, ml, hook_on);
                             else if (L.n_halves == 2) {
-                                if (l == 0) fwd_epilogue_layer<8, 0, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 0 * kW), a8, wsig_c, wrgb_c, hacc, ml);
-                                else fwd_epilogue_layer<8, 0, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 2 * kW), a8, wsig_c, wrgb_c, hacc, ml);
+                                if (l == 0) fwd_epilogue_layer<8, 0, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 0 * kW), a8, wsig_c, wrgb_c, hacc, ml, hook_on);
+                                else fwd_epilogue_layer<8, 0, true, true, 2, kHeadSrc>(taddr, crow_ptr(kCrowBias + 2 * kW), a8, wsig_c, wrgb_c, hacc, ml, hook_on);
                             } else {
                                 const float* bias = crow_ptr(kCrowBias + 3 * kW);
                                 if (p.fuse_comp) {
-                                    if (store) fwd_epilogue_layer<4, 2, true, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                    if (store) fwd_epilogue_layer<4, 2, true, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_last);
                                     else fwd_epilogue_layer<4, 2, false, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                                 }
-                                else if (store) fwd_epilogue_layer<4, 0, true, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
+                                else if (store) fwd_epilogue_layer<4, 0, true, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_last);
                                 else fwd_epilogue_layer<4, 0, false, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                             }
                         }
@@ -831,6 +864,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                                 if (c8 < 8) st_shared_v4_off<0>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
                                 else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
                             }
+                            if (c8 == 7) hook_on(0);
+                            if (c8 == 15) hook_on(1);
                         }
                     }
                     if (head_mma) {
@@ -864,9 +899,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         wait_buf_free();
                         const uint32_t* ml = mset + (size_t)(B.mask_layer >= 0 ? B.mask_layer : 0) * 8 * kTileRows;
                         const float* wsig_s = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWsig) : smem_fptr(sWsig, order_token());
-                        if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
-                        else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
-                        else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep);
+                        if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep, hook_on);
+                        else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep, hook_on);
+                        else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep, hook_on);
                         publish(s + 1 < ns);
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | (nl + s - 1));
                         tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
@@ -1455,6 +1490,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.d_wrgb2 = d_params ? d_params + L.rgb2_w : nullptr; bp.d_brgb2 = d_params ? d_params + L.rgb2_b : nullptr;
     bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise
     bp.keep_weights = cnb_option("keep_weights", 1) != 0 ? 1 : 0;
+    bp.stash_early = cnb_option("stash_early", 1) != 0 ? 1 : 0;
     bp.stash_copy = cnb_option("stash_copy", 0) != 0 ? 1 : 0;      // measured slower (K2 9.9 vs 8.6 ms): one warp's LSU rate
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux

@@ -270,10 +270,14 @@ __device__ __forceinline__ void tmem_regs_ready(uint32_t (&r)[32]) {
 // pipeline, the next two loads are issued before the current two chunks are processed, so only the first wait of a
 // layer exposes the TMEM latency (~300 cycles each; with CTA pairs the kernels' period is MMA + epilogue, so the
 // epilogue's stalls count -- in round 1, when the weight ring set the period, this measured +-0).
-template <int NCC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC, bool DEEP = false>
+struct NoBlockHook { __device__ __forceinline__ void operator()(int) const {} };
+// `hook(b)` is called as soon as 64-column block b of the next operand is complete in shared memory (K2 hands it to
+// the auxiliary warp's bulk store then, instead of after the whole layer).
+template <int NCC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC, bool DEEP = false, class Hook = NoBlockHook>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
-                                                   const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr) {
+                                                   const float* __restrict__ w_rgb2, HeadAcc& acc, uint32_t* mscr,
+                                                   Hook hook = Hook()) {
     if constexpr (DEEP && NCC == 8) {
         uint32_t ra[32], rb[32], rc[32], rd[32];
         umma::tmem_ld32(taddr + 0, ra);
@@ -284,22 +288,26 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         umma::tmem_ld32(taddr + 96, rd);
         fwd_epilogue32<0, KIND, STORE, MASK, SRC, HSRC>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
         fwd_epilogue32<1, KIND, STORE, MASK, SRC, HSRC>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        hook(0);
         umma::tmem_ld_wait();
         tmem_regs_ready(rc); tmem_regs_ready(rd);
         umma::tmem_ld32(taddr + 128, ra);
         umma::tmem_ld32(taddr + 160, rb);
         fwd_epilogue32<2, KIND, STORE, MASK, SRC, HSRC>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
         fwd_epilogue32<3, KIND, STORE, MASK, SRC, HSRC>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        hook(1);
         umma::tmem_ld_wait();
         tmem_regs_ready(ra); tmem_regs_ready(rb);
         umma::tmem_ld32(taddr + 192, rc);
         umma::tmem_ld32(taddr + 224, rd);
         fwd_epilogue32<4, KIND, STORE, MASK, SRC, HSRC>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr);
         fwd_epilogue32<5, KIND, STORE, MASK, SRC, HSRC>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        hook(2);
         umma::tmem_ld_wait();
         tmem_regs_ready(rc); tmem_regs_ready(rd);
         fwd_epilogue32<6, KIND, STORE, MASK, SRC, HSRC>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
         fwd_epilogue32<7, KIND, STORE, MASK, SRC, HSRC>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
+        hook(3);
         return;
     }
 #if CNB_EPI_PREFETCH
@@ -316,6 +324,7 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         umma::tmem_ld_wait();
         fwd_epilogue32<CC, KIND, STORE, MASK, SRC, HSRC, P, P>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
         fwd_epilogue32<CC + 1, KIND, STORE, MASK, SRC, HSRC, P, P && (CC + 2 < NCC)>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
+        hook(CC >> 1);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
