@@ -46,6 +46,7 @@ Opt g_opts[] = {
     {"stash_copy", false, 0},     // 1: the auxiliary warp copies the stash with ld.shared / st.global instead of TMA bulk stores (slower)
     {"stash_lanes", false, 0},    // bulk stores per stashed operand image (32 = 2 KB pieces; 1, 2, 4, 8, 16)
     {"stash_early", false, 0},    // 0: one stash hand-off per operand image (after the whole epilogue) instead of one per 64-column block
+    {"early_pieces", false, 0},   // bulk stores per signalled block of the early stash (1, 2, 4, 8)
     {"experiment", false, 0},     // timing experiments (bit mask, WRONG results): 1 no stash stores, 2 group Y reuses group X's weight fills
     {"stash_wrap", false, 0},     // timing experiment: stash tile t in slot t % value (stays in L2; gradients are WRONG)
 };

@@ -94,6 +94,7 @@ struct BwdParams {
     int keep_weights;               // 1: weight loads carry an L2 evict_last policy while the stash streams through L2
     int stash_early;                // 1: every 64-column block of an operand image is handed to the auxiliary warp's bulk store as soon as
                                     // the epilogue has written it (4 signals per image instead of 1): the store drains during the epilogue
+    int early_pieces;               // (stash_early) bulk stores per signalled part, one lane each
     int stash_copy;                 // 1: the auxiliary warp copies the image itself (ld.shared + st.global), off the TMA queue
     int experiment;                 // timing experiments (option experiment, WRONG results): bit 0 no stash stores, bit 1 no weight fills for group 1
     int64_t stash_wrap;             // timing experiment (option stash_wrap): tile t is stashed in slot t % stash_wrap (WRONG gradients)
@@ -304,10 +305,11 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
         umma::tmem_ld32(taddr + CC * 32 + 32, rb);
         const uint32_t m0 = HAS_MASK ? umma::ld_global_hint(mscr + (size_t)CC * kTileRows, pol) : 0xffffffffu;
         const uint32_t m1 = HAS_MASK ? umma::ld_global_hint(mscr + (size_t)(CC + 1) * kTileRows, pol) : 0xffffffffu;
+        if constexpr (CC > 0) hook((CC >> 1) - 1);      // the previous block is handed over while this pair's loads travel
         umma::tmem_ld_wait();
         bwd_epilogue32<CC, HAS_MASK, ADD_SIGMA>(ra, a8, m0, dsp2, w_sigma);
         bwd_epilogue32<CC + 1, HAS_MASK, ADD_SIGMA>(rb, a8, m1, dsp2, w_sigma);
-        hook(CC >> 1);
+        if constexpr (CC == 6) hook(3);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -525,11 +527,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             } else if (early) {
                 // block by block, as the epilogue signals them (block 0 arrived with aux_ready): the image drains while the
                 // rest of it is still being written, so the buffer is free again by the time the next epilogue needs it
-                for (int b = 0; b < blocks; ++b) {
+                const int n_sig = (p.stash_early == 2 && blocks > 1) ? blocks / 2 : blocks;      // (stash_early 2: one signal per two blocks)
+                const uint32_t part = (uint32_t)(blocks / n_sig) * kABlock;
+                for (int b = 0; b < n_sig; ++b) {
                     if (b > 0) { CNB_TR(tr_wx, umma::mbar_wait(&aux_blk[g * 3 + b - 1], apb[b - 1] & 1u)); ++apb[b - 1]; }
-                    if (stash && !(p.experiment & 1) && lane == 0) {
-                        umma::bulk_s2g_hint(dst + (size_t)b * kABlock, src + (size_t)b * kABlock, kABlock, pol_stream);
-                        if (phs == 0) umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
+                    if (stash && !(p.experiment & 1) && lane < p.early_pieces) {
+                        const uint32_t piece = part / (uint32_t)p.early_pieces;
+                        umma::bulk_s2g_hint(dst + (size_t)b * part + (size_t)lane * piece, src + (size_t)b * part + (size_t)lane * piece, piece, pol_stream);
+                        if (phs == 0 && lane == 0) umma::bulk_s2g_hint(p.stashA + (size_t)tile * p.a_tile_bytes + p.dir_slot, sA + 4 * kABlock, kDirBlock, pol_stream);
                         umma::bulk_commit();
                     }
                     __syncwarp();
@@ -634,12 +639,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const bool early = p.stash && p.stash_early && !p.stash_copy;
         // (stash_early) block b of the operand image being written is complete: hand it to the auxiliary warp
         auto block_done = [&](int b) {
-            umma::fence_proxy_async_smem();
+            if (!(p.experiment & 32)) umma::fence_proxy_async_smem();      // (bit 5: timing experiment without the proxy fence)
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(b == 0 ? &aux_ready[g] : &aux_blk[g * 3 + b - 1]);
         };
-        auto hook_on = [&](int b) { if (early) block_done(b); };
-        auto hook_last = [&](int b) { if (early && !head_mma) block_done(b); };      // rgb.0's output is only stashed for the head kernel
+        const bool by2 = p.stash_early == 2;      // one signal per two blocks (every phase the hooks serve has 2 or 4 blocks)
+        auto hook_on = [&](int b) { if (early) { if (!by2) block_done(b); else if (b & 1) block_done(b >> 1); } };
+        auto hook_last = [&](int b) { if (early && !head_mma) { if (!by2) block_done(b); else if (b & 1) block_done(b >> 1); } };      // rgb.0's output is only stashed for the head kernel
         auto publish = [&](bool to_mma) {
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
@@ -701,7 +707,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     wait_buf_free();
                     pe_store_xyz(pe.x, sA, row);
                     pe_store_dir(pe.d, sA + 4 * kABlock, row);
-                    hook_on(0);
+                    if (early) block_done(0);
                     publish(true);
                     if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (6 << 12) | (g << 8));               // encodings stored: tile starts
                     tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
@@ -1490,7 +1496,8 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.d_wrgb2 = d_params ? d_params + L.rgb2_w : nullptr; bp.d_brgb2 = d_params ? d_params + L.rgb2_b : nullptr;
     bp.stash_lanes = 0;      // decided below: 2 on CTA pairs, 32 otherwise
     bp.keep_weights = cnb_option("keep_weights", 1) != 0 ? 1 : 0;
-    bp.stash_early = cnb_option("stash_early", 1) != 0 ? 1 : 0;
+    { const int64_t se = cnb_option("stash_early", 1); bp.stash_early = se == 2 ? 2 : (se != 0 ? 1 : 0); }
+    { const int64_t ep = cnb_option("early_pieces", 1); bp.early_pieces = (ep == 2 || ep == 4 || ep == 8) ? (int)ep : 1; }
     bp.stash_copy = cnb_option("stash_copy", 0) != 0 ? 1 : 0;      // measured slower (K2 9.9 vs 8.6 ms): one warp's LSU rate
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux

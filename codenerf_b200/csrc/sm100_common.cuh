@@ -321,10 +321,11 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         uint32_t ra[32], rb[32];
         umma::tmem_ld32(taddr + CC * 32, ra);
         umma::tmem_ld32(taddr + CC * 32 + 32, rb);
+        if constexpr (CC > 0) hook((CC >> 1) - 1);      // the previous block is handed over while this pair's TMEM loads travel
         umma::tmem_ld_wait();
         fwd_epilogue32<CC, KIND, STORE, MASK, SRC, HSRC, P, P>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
         fwd_epilogue32<CC + 1, KIND, STORE, MASK, SRC, HSRC, P, P && (CC + 2 < NCC)>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
-        hook(CC >> 1);
+        if constexpr (CC + 2 >= NCC) hook(CC >> 1);
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
