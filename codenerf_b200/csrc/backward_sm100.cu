@@ -38,6 +38,9 @@ constexpr int kHeadSrc = CNB_K2_HEADS_CONST ? 2 : 1;
 #endif
 constexpr bool kDeep = CNB_K2_DEEP_LD != 0;
 
+#ifndef CNB_EARLY_NAMED
+#define CNB_EARLY_NAMED 0      // 1: early-stash hand-offs on hardware named barriers instead of mbarriers (measured: no faster)
+#endif
 #ifdef CNB_TRACE
 extern "C" int cnb_debug_events_bwd(unsigned long long* out, unsigned int* counts, int reset) {
     if (out && cudaMemcpyFromSymbol(out, sm100::g_events, sizeof(unsigned long long) * 4 * 16384) != cudaSuccess) return -1;
@@ -487,7 +490,14 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const bool early = p.stash && p.stash_early && !p.stash_copy;
         uint32_t apb[3] = {0u, 0u, 0u};       // phases consumed of aux_blk[g][0..2]
         auto phase = [&](int64_t tile, bool live, int phs) {
+#if CNB_EARLY_NAMED
+            // (stash_early) hardware named barriers 4 + 4 g + b: 128 epilogue threads arrive, this warp syncs -- no
+            // elected-lane branch and shared-memory atomic on the epilogue side, no polling here
+            if (early) { CNB_TR(tr_wx, umma::named_bar_sync(4 + 4 * g, 160)); }
+            else { CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap; }
+#else
             CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
+#endif
             const bool stash = p.stash && live;
             if (p.stash_wrap > 0) tile %= p.stash_wrap;
             // with the in-kernel rgb.2 gradient step 0 writes blocks 2-3 (blocks 0-1 still hold r1 for that MMA)
@@ -530,7 +540,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 const int n_sig = (p.stash_early == 2 && blocks > 1) ? blocks / 2 : blocks;      // (stash_early 2: one signal per two blocks)
                 const uint32_t part = (uint32_t)(blocks / n_sig) * kABlock;
                 for (int b = 0; b < n_sig; ++b) {
+#if CNB_EARLY_NAMED
+                    if (b > 0) { CNB_TR(tr_wx, umma::named_bar_sync(4 + 4 * g + b, 160)); }
+#else
                     if (b > 0) { CNB_TR(tr_wx, umma::mbar_wait(&aux_blk[g * 3 + b - 1], apb[b - 1] & 1u)); ++apb[b - 1]; }
+#endif
                     if (stash && !(p.experiment & 1) && lane < p.early_pieces) {
                         const uint32_t piece = part / (uint32_t)p.early_pieces;
                         umma::bulk_s2g_hint(dst + (size_t)b * part + (size_t)lane * piece, src + (size_t)b * part + (size_t)lane * piece, piece, pol_stream);
@@ -640,8 +654,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         // (stash_early) block b of the operand image being written is complete: hand it to the auxiliary warp
         auto block_done = [&](int b) {
             if (!(p.experiment & 32)) umma::fence_proxy_async_smem();      // (bit 5: timing experiment without the proxy fence)
+#if CNB_EARLY_NAMED
+            umma::named_bar_arrive(4 + 4 * g + b, 160);
+#else
             __syncwarp();
             if (lane == 0) umma::mbar_arrive(b == 0 ? &aux_ready[g] : &aux_blk[g * 3 + b - 1]);
+#endif
         };
         const bool by2 = p.stash_early == 2;      // one signal per two blocks (every phase the hooks serve has 2 or 4 blocks)
         auto hook_on = [&](int b) { if (early) { if (!by2) block_done(b); else if (b & 1) block_done(b >> 1); } };
