@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         float4* ring = sRing + g * 2 * kTileRows;
         uint32_t bsel = 0;                               // staging buffer of the next layer (alternates)
 
-        CNB_TR_DECL(tr_wbuf); CNB_TR_DECL(tr_wacc_f); CNB_TR_DECL(tr_epi_f); CNB_TR_DECL(tr_mid); CNB_TR_DECL(tr_wacc_b);
+        CNB_TR_DECL(tr_wbuf); CNB_TR_DECL(tr_wacc_f); CNB_TR_DECL(tr_epi_f); CNB_TR_DECL(tr_mid); CNB_TR_DECL(tr_mid_f); CNB_TR_DECL(tr_headw); CNB_TR_DECL(tr_wacc_b);
         CNB_TR_DECL(tr_epi_b); CNB_TR_DECL(tr_enc); CNB_TR_DECL(tr_tot);
         const long long tr_t0 = CNB_TR_NOW();
         auto wait_buf_free = [&]() { if (wp > 0) CNB_TR(tr_wbuf, umma::mbar_wait(&buf_free[g], (wp - 1) & 1u)); };
@@ -675,33 +675,46 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
             ++wp;
         };
 
-        // rays / samples / positional encodings of one tile (tile < 0: none), as packed bf16 rows in registers
-        auto prepare_tile = [&](int64_t tile, PeRow& pe) {
+        // rays / samples of one tile (tile < 0: none), then their positional encodings as packed bf16 rows in registers.
+        // Two steps so that each fits inside ONE GEMM wait of the backward chain (together they took ~4.5 K cycles against a
+        // ~2.8 K wait: the trace showed the accumulator of that step picked up 2-4 K cycles late).
+        struct RaySample { float pos[3], dir[3]; bool ok; };
+        auto fetch_tile = [&](int64_t tile, RaySample& rsm) {
             const int64_t lr = tile * kTileRows + row;
-            const bool ok = tile >= 0 && lr < p.S;
-            float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
-            if (ok) {
+            rsm.ok = tile >= 0 && lr < p.S;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { rsm.pos[k] = 0.f; rsm.dir[k] = 0.f; }
+            if (rsm.ok) {
                 if (p.mode == 0) {
                     const int64_t gr = p.row_offset + lr;
                     const int64_t ray = gr / N;
                     const int zi = (int)(gr - ray * N);
                     float o[3];
-                    cnb_fetch_ray(p.rs, ray, o, dir);
+                    cnb_fetch_ray(p.rs, ray, o, rsm.dir);
                     const int64_t seg = ray / p.rs.rays_per_segment;
                     const float z = __ldg(p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0) + zi);
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) pos[k] = cnb_sample_coord(o[k], dir[k], z);
+                    for (int k = 0; k < 3; ++k) rsm.pos[k] = cnb_sample_coord(o[k], rsm.dir[k], z);
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 3; ++k) { pos[k] = __ldg(p.xyz + lr * 3 + k); dir[k] = __ldg(p.viewdir + lr * 3 + k); }
+                    for (int k = 0; k < 3; ++k) { rsm.pos[k] = __ldg(p.xyz + lr * 3 + k); rsm.dir[k] = __ldg(p.viewdir + lr * 3 + k); }
                 }
             }
-            pe_compute_xyz(pos, ok, pe.x);
-            pe_compute_dir(dir, ok, pe.d);
         };
+        auto encode_tile = [&](const RaySample& rsm, PeRow& pe) {
+            pe_compute_xyz(rsm.pos, rsm.ok, pe.x);
+            pe_compute_dir(rsm.dir, rsm.ok, pe.d);
+        };
+        auto prepare_tile = [&](int64_t tile, PeRow& pe) { RaySample rsm; fetch_tile(tile, rsm); encode_tile(rsm, pe); };
         // first tile of unit slot u of this group (-1: none; phantom units encode all-zero rows)
         auto unit_tile0 = [&](int u) -> int64_t { return (u < UN && u < UN_own) ? (unit0 + u) * U : (int64_t)-1; };
         PeRow pe;
+        RaySample next_rays;
+#ifdef CNB_PE_ONE_STEP      // (A/B: both halves inside the same wait, as before)
+        const int s_fetch = ns > 3 ? 3 : 1, s_encode = s_fetch;
+#else
+        const int s_fetch = ns > 3 ? 3 : 1, s_encode = ns > 5 ? 5 : s_fetch;
+#endif      // backward steps whose GEMM waits hide the two halves
         bool pe_ready = false;
         if (g < UN) { prepare_tile(unit_tile0(g), pe); pe_ready = true; }
 
@@ -811,7 +824,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             composite_fwd_bwd(p, ring, (j * N) & 255, phantom ? p.n_rays_total : ray_unit0 + j, lane);
                         umma::named_bar_sync(1 + g, 128);
                     }
-                    tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
+                    tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0); tr_mid_f += (unsigned long long)(CNB_TR_NOW() - tr_m0);
                 } else {
                     const uint32_t* mb = mscr + (size_t)((i - LA) & 1) * mask_set;       // i == U: only with lookahead
 #pragma unroll
@@ -894,7 +907,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     }
                     if (head_mma) {
                         // the small MMA has had the whole of step 0 to finish: D[m = row][0..5] = sum over the tile's rows
-                        CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
+                        CNB_TR(tr_headw, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
                         umma::tc_fence_after();
                         uint32_t d8[8];
                         umma::tmem_ld8(taddr + (CG == 2 ? rank * 32u : 0u), d8);
@@ -915,7 +928,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     const uint64_t dsp2 = pk2f(dspre, dspre);
                     for (int s = 1; s < ns; ++s) {
                         const BwdStep& B = p.steps[s];
-                        if (s == (ns > 3 ? 3 : 1) && next_tile != -2) { prepare_tile(next_tile, pe); pe_ready = true; }
+                        if (next_tile != -2) {
+                            if (s == s_fetch) fetch_tile(next_tile, next_rays);
+                            if (s == s_encode) { encode_tile(next_rays, pe); pe_ready = true; }
+                        }
                         CNB_TR(tr_wacc_b, umma::mbar_wait(&acc_full[g], opc & 1u)); ++opc;
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (3 << 12) | (g << 8) | (nl + s - 1));
                         const long long tr_b0 = CNB_TR_NOW();
@@ -945,6 +961,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         if (warp == 4) {
             CNB_TR_FLUSH(5, tr_wbuf); CNB_TR_FLUSH(6, tr_wacc_f); CNB_TR_FLUSH(7, tr_epi_f); CNB_TR_FLUSH(8, tr_mid);
             CNB_TR_FLUSH(9, tr_wacc_b); CNB_TR_FLUSH(10, tr_epi_b); CNB_TR_FLUSH(11, tr_enc); CNB_TR_FLUSH(12, tr_tot);
+            CNB_TR_FLUSH(13, tr_mid_f); CNB_TR_FLUSH(14, tr_headw);
         }
     }
     umma::tc_fence_before();

@@ -24,7 +24,7 @@ rb = bundle.args(sc, tc)
 tgt = torch.rand(n_seg * R, 3, device="cuda")
 nl, n_ops = 8, 15
 names = ["mma.wait_a_ready", "mma.wait_w_full", "mma.total", "auxX.wait_ready", "auxX.total", "X.wait_buf_free", "X.wait_acc_fwd",
-         "X.epilogue_fwd(+buf)", "X.composite+step0", "X.wait_acc_bwd", "X.epilogue_bwd(+buf)", "X.encode", "X.total"]
+         "X.epilogue_fwd(+buf)", "X.composite+step0", "X.wait_acc_bwd", "X.epilogue_bwd(+buf)", "X.encode", "X.total", "X.mid: composite part", "X.mid: head MMA wait"]
 fbuf = (ctypes.c_float * 512)()
 tbuf = (ctypes.c_ulonglong * 32)()
 ev = (ctypes.c_ulonglong * (4 * 16384))(); cnt = (ctypes.c_uint * 4)()
