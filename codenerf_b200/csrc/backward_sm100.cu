@@ -38,6 +38,9 @@ constexpr int kHeadSrc = CNB_K2_HEADS_CONST ? 2 : 1;
 #endif
 constexpr bool kDeep = CNB_K2_DEEP_LD != 0;
 
+#ifndef CNB_L0_ROTATE
+#define CNB_L0_ROTATE 0        // 1: the first layer's epilogue writes operand block 0 (the encodings, still draining to the stash) last (measured: slower)
+#endif
 #ifndef CNB_EARLY_NAMED
 #define CNB_EARLY_NAMED 0      // 1: early-stash hand-offs on hardware named barriers instead of mbarriers (measured: no faster)
 #endif
@@ -140,18 +143,19 @@ __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 
 // in the group's 256-entry sample ring (two tiles) at ring[(start + k) & 255], k < N <= 128, so a ray may straddle
 // two tiles; the per-sample seeds (d sigma, d r, d g, d b) overwrite them in place.  Any N in [1, 128]: lane l owns
 // samples [l * per, l * per + per) with per = ceil(N / 32); samples past N are identities of both scans.
-__device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, float4* ring, int start, int64_t gray, int lane) {
+template <int PER>
+__device__ __noinline__ void composite_fwd_bwd_t(const BwdParams& p, float4* ring, int start, int64_t gray, int lane) {
     const int N = p.rs.N;
-    const int per = (N + 31) >> 5;
+    constexpr int per = PER;
     const int i0 = lane * per;
     const bool live = gray < p.n_rays_total;
     const int64_t seg = (live ? gray : 0) / p.rs.rays_per_segment;
     const float* z = p.rs.z_vals + (p.rs.z_per_segment ? seg * N : 0);
-    float alpha[4], tt[4], dl[4], ex[4], zz[4];
-    float4 s[4];
+    float alpha[PER], tt[PER], dl[PER], ex[PER], zz[PER];
+    float4 s[PER];
     float tl = 1.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < PER; ++j) {
         alpha[j] = 0.f; tt[j] = 1.f; dl[j] = 0.f; ex[j] = 0.f; zz[j] = 0.f; s[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int i = i0 + j;
         if (j < per && i < N) {
@@ -170,11 +174,11 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, float4* ring,
     for (int d = 1; d < 32; d <<= 1) { const float up = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl *= up; }
     float T0 = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) T0 = 1.f;
-    float Tj[4], cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, ws = 0.f;
+    float Tj[PER], cr = 0.f, cg = 0.f, cb = 0.f, dep = 0.f, ws = 0.f;
     {
         float T = T0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < PER; ++j) {
             Tj[j] = T;
             const float w = alpha[j] * T;
             cr += w * s[j].y; cg += w * s[j].z; cb += w * s[j].w; dep += w * zz[j]; ws += w;
@@ -204,10 +208,10 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, float4* ring,
     }
     // reverse mode: aT_i = g_i alpha_i + t_i aT_{i+1}; d alpha_i = (g_i - aT_{i+1}) T_i   (division free)
     const float bg = p.white_bg ? 1.f : 0.f;
-    float gsm[4];
+    float gsm[PER];
     float A = 1.f, Bc = 0.f;
 #pragma unroll
-    for (int j = 3; j >= 0; --j) {
+    for (int j = PER - 1; j >= 0; --j) {
         gsm[j] = gr * (s[j].y - bg) + gg * (s[j].z - bg) + gb * (s[j].w - bg) + gd * zz[j];
         Bc = gsm[j] * alpha[j] + tt[j] * Bc;
         A = tt[j] * A;
@@ -222,11 +226,21 @@ __device__ __noinline__ void composite_fwd_bwd(const BwdParams& p, float4* ring,
     float aT_next = __shfl_down_sync(0xffffffffu, sB, 1);
     if (lane == 31) aT_next = 0.f;
 #pragma unroll
-    for (int j = 3; j >= 0; --j) {
+    for (int j = PER - 1; j >= 0; --j) {
         const float w = alpha[j] * Tj[j];
         const float a_alpha = (gsm[j] - aT_next) * Tj[j];
         if (j < per && i0 + j < N) ring[(start + i0 + j) & 255] = make_float4(a_alpha * dl[j] * ex[j], w * gr, w * gg, w * gb);
         aT_next = gsm[j] * alpha[j] + aT_next * tt[j];
+    }
+}
+
+// samples per lane = ceil(N / 32) as a compile-time constant: the per-lane loops carry no dead (predicated-off) iterations
+__device__ __forceinline__ void composite_fwd_bwd(const BwdParams& p, float4* ring, int start, int64_t gray, int lane) {
+    switch ((p.rs.N + 31) >> 5) {
+        case 1: composite_fwd_bwd_t<1>(p, ring, start, gray, lane); break;
+        case 2: composite_fwd_bwd_t<2>(p, ring, start, gray, lane); break;
+        case 3: composite_fwd_bwd_t<3>(p, ring, start, gray, lane); break;
+        default: composite_fwd_bwd_t<4>(p, ring, start, gray, lane); break;
     }
 }
 
@@ -490,14 +504,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const bool early = p.stash && p.stash_early && !p.stash_copy;
         uint32_t apb[3] = {0u, 0u, 0u};       // phases consumed of aux_blk[g][0..2]
         auto phase = [&](int64_t tile, bool live, int phs) {
-#if CNB_EARLY_NAMED
-            // (stash_early) hardware named barriers 4 + 4 g + b: 128 epilogue threads arrive, this warp syncs -- no
-            // elected-lane branch and shared-memory atomic on the epilogue side, no polling here
-            if (early) { CNB_TR(tr_wx, umma::named_bar_sync(4 + 4 * g, 160)); }
-            else { CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap; }
-#else
-            CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap;
-#endif
+            // (stash_early: the blocks are waited for one by one below, block 0 not necessarily first)
+            if (!early) { CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap; }
             const bool stash = p.stash && live;
             if (p.stash_wrap > 0) tile %= p.stash_wrap;
             // with the in-kernel rgb.2 gradient step 0 writes blocks 2-3 (blocks 0-1 still hold r1 for that MMA)
@@ -539,11 +547,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 // rest of it is still being written, so the buffer is free again by the time the next epilogue needs it
                 const int n_sig = (p.stash_early == 2 && blocks > 1) ? blocks / 2 : blocks;      // (stash_early 2: one signal per two blocks)
                 const uint32_t part = (uint32_t)(blocks / n_sig) * kABlock;
-                for (int b = 0; b < n_sig; ++b) {
+                const bool rot = CNB_L0_ROTATE && phs == 1 && n_sig == 4 && !kDeep && !CNB_K2_BIAS_CONST && p.layers[0].kind == 0 && p.layers[0].n_halves == 2;
+                for (int bi = 0; bi < n_sig; ++bi) {
+                    const int b = rot ? ((bi + 1) & 3) : bi;      // layer 0's output arrives in the block order 1, 2, 3, 0
 #if CNB_EARLY_NAMED
-                    if (b > 0) { CNB_TR(tr_wx, umma::named_bar_sync(4 + 4 * g + b, 160)); }
+                    // hardware named barriers 4 + 4 g + b: 128 epilogue threads arrive, this warp syncs (measured: no faster)
+                    CNB_TR(tr_wx, umma::named_bar_sync(4 + 4 * g + b, 160));
 #else
                     if (b > 0) { CNB_TR(tr_wx, umma::mbar_wait(&aux_blk[g * 3 + b - 1], apb[b - 1] & 1u)); ++apb[b - 1]; }
+                    else { CNB_TR(tr_wx, umma::mbar_wait(&aux_ready[g], ap & 1u)); ++ap; }
 #endif
                     if (stash && !(p.experiment & 1) && lane < p.early_pieces) {
                         const uint32_t piece = part / (uint32_t)p.early_pieces;
@@ -759,7 +771,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         umma::tc_fence_after();
                         const bool last = (l + 1 == nl);
                         const bool store = !last || p.stash;
-                        if (store) wait_buf_free();
+                        // layer 0 of a full-width chain drains in the block order 1, 2, 3, 0 and waits for the buffer (the stash
+                        // store of the encodings, issued one K = 64 GEMM ago) only before block 0
+                        const bool rot = CNB_L0_ROTATE && l == 0 && !kDeep && staged && L.kind == 0 && L.n_halves == 2 && store && !by2;
+                        if (store && !rot) wait_buf_free();
                         uint32_t* ml = mset + (size_t)l * 8 * kTileRows;
                         // head weights: constant memory, or the shared-memory copy (a per-layer token keeps the loads inside the layer)
                         const uint32_t htok = CNB_K2_HEADS_CONST ? 0u : order_token();
@@ -771,6 +786,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             const uint32_t tok = bar_sync_token(1 + g, 128);
                             const float* bias = smem_fptr(sb, tok);
                             if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on);
+                            else if (rot) fwd_epilogue_layer_rot<0, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on, wait_buf_free);
                             else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on);
                             else if (p.fuse_comp) {
                                 if (store) fwd_epilogue_layer<4, 2, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_last);
@@ -877,16 +893,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     {
                         const float* wrgb_s = CNB_K2_HEADS_CONST ? crow_ptr(kCrowWrgb) : smem_fptr(sWrgb, order_token());
                         const uint64_t r2 = pk2f(dcr, dcr), g2 = pk2f(dcg, dcg), b2 = pk2f(dcb, dcb);
+                        // the rgb.2 rows of column group c8 + 1 are loaded before group c8 is stored (see fwd_epilogue32)
+                        float4 wn[6];
+#pragma unroll
+                        for (int hh = 0; hh < 2; ++hh) {
+                            wn[hh * 3 + 0] = ld_vec4<kHeadSrc>(wrgb_s + hh * 4);
+                            wn[hh * 3 + 1] = ld_vec4<kHeadSrc>(wrgb_s + (kW / 2) + hh * 4);
+                            wn[hh * 3 + 2] = ld_vec4<kHeadSrc>(wrgb_s + kW + hh * 4);
+                        }
 #pragma unroll
                         for (int c8 = 0; c8 < 16; ++c8) {
                             const uint32_t mlast = mlast4[c8 >> 2];
                             const int col = c8 * 8;
                             uint32_t w[4];
+                            float4 wc[6];
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) wc[k] = wn[k];
+                            if (c8 + 1 < 16) {
+#pragma unroll
+                                for (int hh = 0; hh < 2; ++hh) {
+                                    wn[hh * 3 + 0] = ld_vec4<kHeadSrc>(wrgb_s + col + 8 + hh * 4);
+                                    wn[hh * 3 + 1] = ld_vec4<kHeadSrc>(wrgb_s + (kW / 2) + col + 8 + hh * 4);
+                                    wn[hh * 3 + 2] = ld_vec4<kHeadSrc>(wrgb_s + kW + col + 8 + hh * 4);
+                                }
+                            }
 #pragma unroll
                             for (int hh = 0; hh < 2; ++hh) {
-                                const float4 w0 = ld_vec4<kHeadSrc>(wrgb_s + col + hh * 4);
-                                const float4 w1 = ld_vec4<kHeadSrc>(wrgb_s + (kW / 2) + col + hh * 4);
-                                const float4 w2 = ld_vec4<kHeadSrc>(wrgb_s + kW + col + hh * 4);
+                                const float4 w0 = wc[hh * 3 + 0], w1 = wc[hh * 3 + 1], w2 = wc[hh * 3 + 2];
                                 uint64_t v0 = ffma2(r2, pk2f(w0.x, w0.y), ffma2(g2, pk2f(w1.x, w1.y), ffma2(b2, pk2f(w2.x, w2.y), 0ull)));
                                 uint64_t v1 = ffma2(r2, pk2f(w0.z, w0.w), ffma2(g2, pk2f(w1.z, w1.w), ffma2(b2, pk2f(w2.z, w2.w), 0ull)));
                                 // columns col + 4 hh .. + 3 of the chunk: word << ((col & 31) / 4 + hh), both byte pairs

@@ -335,6 +335,38 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
     }
 }
 
+// A 256-column layer drained in the block order 1, 2, 3, 0 (non-DEEP form).  For the FIRST layer of a tile: block 0 of the
+// operand buffer still holds the positional encodings whose stash store was issued one short (K = 64) GEMM ago;
+// `before_block0()` (the wait for that store) is called only when the other three blocks are done.
+template <int KIND, bool MASK, int SRC, int HSRC, class Hook, class BeforeBlock0>
+__device__ __forceinline__ void fwd_epilogue_layer_rot(uint32_t taddr, const float* __restrict__ bias, const uint32_t (&a8)[8],
+                                                       const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
+                                                       HeadAcc& acc, uint32_t* mscr, Hook hook, BeforeBlock0 before_block0) {
+    constexpr bool P = CNB_EPI_PREFETCH != 0;
+#if CNB_EPI_PREFETCH
+    float4 pre[2] = {ld_vec4<SRC>(bias + 64), ld_vec4<SRC>(bias + 68)};
+#else
+    float4* pre = nullptr;
+#endif
+    auto pair = [&](auto cc_tag, auto first_tag) {
+        constexpr int CC = decltype(cc_tag)::value;
+        constexpr bool FIRST = decltype(first_tag)::value;      // first pair of the rotated order (CC = 2)
+        uint32_t ra[32], rb[32];
+        umma::tmem_ld32(taddr + CC * 32, ra);
+        umma::tmem_ld32(taddr + CC * 32 + 32, rb);
+        if constexpr (!FIRST) hook(CC == 0 ? 3 : (CC >> 1) - 1);      // the block before this one in the rotated order
+        if constexpr (CC == 0) before_block0();
+        umma::tmem_ld_wait();
+        fwd_epilogue32<CC, KIND, true, MASK, SRC, HSRC, P && CC != 0, P>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
+        fwd_epilogue32<CC + 1, KIND, true, MASK, SRC, HSRC, P, P && CC != 0 && CC != 6>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
+        if constexpr (CC == 0) hook(0);
+    };
+    pair(std::integral_constant<int, 2>{}, std::true_type{});
+    pair(std::integral_constant<int, 4>{}, std::false_type{});
+    pair(std::integral_constant<int, 6>{}, std::false_type{});
+    pair(std::integral_constant<int, 0>{}, std::false_type{});
+}
+
 // NC (2 or 4) consecutive 32-column chunks of a layer: one thread's share when two warps split the columns of a row.
 // Every pointer / address argument is pre-offset to the thread's first chunk (so the column half is a run-time
 // value and the code exists once); a8 must point at the K-block that receives the first chunk.

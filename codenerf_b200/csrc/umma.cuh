@@ -128,8 +128,19 @@ __device__ __forceinline__ void st_global_hint(uint32_t* ptr, uint32_t v, uint64
 __device__ __forceinline__ void st_global_v4_hint(void* ptr, uint4 v, uint64_t pol) {
     asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(ptr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
+// (ReLU bit words: 28 KB per tile would sweep the ~27 KB of L1 left beside the shared memory and evict the few lines that
+// do get re-used -- z values, target colours, bias rows; CNB_MASK_L1_NOALLOC=0 restores the allocating form)
+#ifndef CNB_MASK_L1_NOALLOC
+#define CNB_MASK_L1_NOALLOC 1
+#endif
 __device__ __forceinline__ uint32_t ld_global_hint(const uint32_t* ptr, uint64_t pol) {
-    uint32_t v; asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol) : "memory"); return v;
+    uint32_t v;
+#if CNB_MASK_L1_NOALLOC
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol) : "memory");
+#else
+    asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(v) : "l"(ptr), "l"(pol) : "memory");
+#endif
+    return v;
 }
 // shared -> global bulk store with an L2 policy (streaming data that should not displace the working set)
 __device__ __forceinline__ void bulk_s2g_hint(void* gmem_dst, const void* smem_src, uint32_t bytes, uint64_t pol) {
