@@ -41,6 +41,7 @@ Opt g_opts[] = {
     {"k3_overlap", false, 0},     // 1: K3 of sub-batch i on a second stream under K2 of sub-batch i + 1
     {"k3_sms", false, 0},         // SMs left to K3 when overlapped
     {"k3_items_per_sm_x10", false, 0},
+    {"k3_grid", false, 0},        // CTAs of the weight-gradient kernel (0: one per SM)
     {"head_mma", false, 0},       // 0: rgb.2 weight gradient by the separate head kernel from the stash (default 1: inside K2)
     {"keep_weights", false, 0},   // 0: no L2 evict_last policy on the weight loads of the training kernel (default 1)
     {"stash_copy", false, 0},     // 1: the auxiliary warp copies the stash with ld.shared / st.global instead of TMA bulk stores (slower)

@@ -1684,6 +1684,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     const size_t wsmem = 1024 + (size_t)kWgStages * kWgStage + 256;
     CNB_CUDA_TRY(cudaFuncSetAttribute(k_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem));
     int wgrid = items < sms ? items : sms;
+    { const int64_t kg = cnb_option("k3_grid", 0); if (kg > 0 && kg < wgrid) wgrid = (int)kg; }      // (measurement: K3 on fewer SMs)
     if (piped && !last_sub && wgrid > pp->k3_sms) wgrid = pp->k3_sms;      // the last K3 overlaps nothing: whole GPU
     cnb_prof_begin(CNB_K_WGRAD, st2);
     k_wgrad<<<wgrid, kWgThreads, wsmem, st2>>>(wp);
