@@ -38,9 +38,6 @@ constexpr int kHeadSrc = CNB_K2_HEADS_CONST ? 2 : 1;
 #endif
 constexpr bool kDeep = CNB_K2_DEEP_LD != 0;
 
-#ifndef CNB_L0_ROTATE
-#define CNB_L0_ROTATE 0        // 1: the first layer's epilogue writes operand block 0 (the encodings, still draining to the stash) last (measured: slower)
-#endif
 #ifndef CNB_EARLY_NAMED
 #define CNB_EARLY_NAMED 0      // 1: early-stash hand-offs on hardware named barriers instead of mbarriers (measured: no faster)
 #endif
@@ -312,7 +309,6 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
         tmem_regs_ready(rc); tmem_regs_ready(rd);
         bwd_epilogue32<6, HAS_MASK, ADD_SIGMA>(rc, a8, m[6], dsp2, w_sigma);
         bwd_epilogue32<7, HAS_MASK, ADD_SIGMA>(rd, a8, m[7], dsp2, w_sigma);
-        hook(3);
         return;
     }
     auto pair = [&](auto cc_tag) {
@@ -326,7 +322,7 @@ __device__ __forceinline__ void bwd_epilogue_layer(uint32_t taddr, const uint32_
         umma::tmem_ld_wait();
         bwd_epilogue32<CC, HAS_MASK, ADD_SIGMA>(ra, a8, m0, dsp2, w_sigma);
         bwd_epilogue32<CC + 1, HAS_MASK, ADD_SIGMA>(rb, a8, m1, dsp2, w_sigma);
-        if constexpr (CC == 6) hook(3);
+        // (block 3 is handed over by the caller together with the operand's publication)
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -547,9 +543,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                 // rest of it is still being written, so the buffer is free again by the time the next epilogue needs it
                 const int n_sig = (p.stash_early == 2 && blocks > 1) ? blocks / 2 : blocks;      // (stash_early 2: one signal per two blocks)
                 const uint32_t part = (uint32_t)(blocks / n_sig) * kABlock;
-                const bool rot = CNB_L0_ROTATE && phs == 1 && n_sig == 4 && !kDeep && !CNB_K2_BIAS_CONST && p.layers[0].kind == 0 && p.layers[0].n_halves == 2;
-                for (int bi = 0; bi < n_sig; ++bi) {
-                    const int b = rot ? ((bi + 1) & 3) : bi;      // layer 0's output arrives in the block order 1, 2, 3, 0
+                for (int b = 0; b < n_sig; ++b) {
 #if CNB_EARLY_NAMED
                     // hardware named barriers 4 + 4 g + b: 128 epilogue threads arrive, this warp syncs (measured: no faster)
                     CNB_TR(tr_wx, umma::named_bar_sync(4 + 4 * g + b, 160));
@@ -676,13 +670,19 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
         const bool by2 = p.stash_early == 2;      // one signal per two blocks (every phase the hooks serve has 2 or 4 blocks)
         auto hook_on = [&](int b) { if (early) { if (!by2) block_done(b); else if (b & 1) block_done(b >> 1); } };
         auto hook_last = [&](int b) { if (early && !head_mma) { if (!by2) block_done(b); else if (b & 1) block_done(b >> 1); } };      // rgb.0's output is only stashed for the head kernel
-        auto publish = [&](bool to_mma) {
+        // `nblk`: 64-column blocks of the image just written; with the early stash its LAST block is handed to the auxiliary
+        // warp here (one fence and one elected-lane branch for both signals), the others by the hooks
+        auto publish = [&](bool to_mma, int nblk) {
             umma::tc_fence_before();
             umma::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
                 if (to_mma) { if (CG == 2) umma::mbar_arrive_cluster(a_ready_addr0 + g * 8); else umma::mbar_arrive(&a_ready[g]); }
                 if (!early) umma::mbar_arrive(&aux_ready[g]);
+                else {
+                    const int sig = by2 ? (nblk > 1 ? nblk / 2 : 1) - 1 : nblk - 1;      // index of the last signal of this image
+                    umma::mbar_arrive(sig == 0 ? &aux_ready[g] : &aux_blk[g * 3 + sig - 1]);
+                }
             }
             ++wp;
         };
@@ -750,8 +750,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                     wait_buf_free();
                     pe_store_xyz(pe.x, sA, row);
                     pe_store_dir(pe.d, sA + 4 * kABlock, row);
-                    if (early) block_done(0);
-                    publish(true);
+                    publish(true, 1);
                     if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (6 << 12) | (g << 8));               // encodings stored: tile starts
                     tr_enc += (unsigned long long)(CNB_TR_NOW() - tr_e0);
 
@@ -771,10 +770,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         umma::tc_fence_after();
                         const bool last = (l + 1 == nl);
                         const bool store = !last || p.stash;
-                        // layer 0 of a full-width chain drains in the block order 1, 2, 3, 0 and waits for the buffer (the stash
-                        // store of the encodings, issued one K = 64 GEMM ago) only before block 0
-                        const bool rot = CNB_L0_ROTATE && l == 0 && !kDeep && staged && L.kind == 0 && L.n_halves == 2 && store && !by2;
-                        if (store && !rot) wait_buf_free();
+                        if (store) wait_buf_free();
                         uint32_t* ml = mset + (size_t)l * 8 * kTileRows;
                         // head weights: constant memory, or the shared-memory copy (a per-layer token keeps the loads inside the layer)
                         const uint32_t htok = CNB_K2_HEADS_CONST ? 0u : order_token();
@@ -786,7 +782,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             const uint32_t tok = bar_sync_token(1 + g, 128);
                             const float* bias = smem_fptr(sb, tok);
                             if (L.kind == 1) fwd_epilogue_layer<8, 1, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on);
-                            else if (rot) fwd_epilogue_layer_rot<0, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on, wait_buf_free);
                             else if (L.n_halves == 2) fwd_epilogue_layer<8, 0, true, true, 1, kHeadSrc, kDeep>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_on);
                             else if (p.fuse_comp) {
                                 if (store) fwd_epilogue_layer<4, 2, true, true, 1, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml, hook_last);
@@ -810,7 +805,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                                 else fwd_epilogue_layer<4, 0, false, true, 2, kHeadSrc>(taddr, bias, a8, wsig_c, wrgb_c, hacc, ml);
                             }
                         }
-                        if (store && !(last && head_mma)) publish(!last);      // (r1 for the in-kernel rgb.2 gradient is published with the seeds)
+                        if (store && !(last && head_mma)) publish(!last, L.n_halves * 2);      // (r1 for the in-kernel rgb.2 gradient is published with the seeds)
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | l);      // epilogue done, operand published
                         tr_epi_f += (unsigned long long)(CNB_TR_NOW() - tr_p0);
                     }
@@ -935,7 +930,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                                 else st_shared_v4_off<kABlock>(a8[c8 & 7], w[0], w[1], w[2], w[3]);
                             }
                             if (c8 == 7) hook_on(0);
-                            if (c8 == 15) hook_on(1);
                         }
                     }
                     if (head_mma) {
@@ -948,7 +942,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
 #pragma unroll
                         for (int k = 0; k < 3; ++k) hw[k] += __uint_as_float(d8[k]) + __uint_as_float(d8[k + 3]);
                     }
-                    publish(ns > 1);
+                    publish(ns > 1, 2);
                     if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (5 << 12) | (g << 8) | nl);         // compositing + step 0 done
                     tr_mid += (unsigned long long)(CNB_TR_NOW() - tr_m0);
 
@@ -975,7 +969,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         if (B.add_sigma) bwd_epilogue_layer<false, true>(taddr, a8, ml, dsp2, wsig_s, pol_keep, hook_on);
                         else if (B.mask_layer >= 0) bwd_epilogue_layer<true, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep, hook_on);
                         else bwd_epilogue_layer<false, false>(taddr, a8, ml, dsp2, wsig_s, pol_keep, hook_on);
-                        publish(s + 1 < ns);
+                        publish(s + 1 < ns, 4);
                         if ((warp & 3) == 0) CNB_EV(lane, 1 + g, (4 << 12) | (g << 8) | (nl + s - 1));
                         tr_epi_b += (unsigned long long)(CNB_TR_NOW() - tr_b0);
                     }

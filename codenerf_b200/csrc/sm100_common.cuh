@@ -272,7 +272,8 @@ __device__ __forceinline__ void tmem_regs_ready(uint32_t (&r)[32]) {
 // epilogue's stalls count -- in round 1, when the weight ring set the period, this measured +-0).
 struct NoBlockHook { __device__ __forceinline__ void operator()(int) const {} };
 // `hook(b)` is called as soon as 64-column block b of the next operand is complete in shared memory (K2 hands it to
-// the auxiliary warp's bulk store then, instead of after the whole layer).
+// the auxiliary warp's bulk store then, instead of after the whole layer) -- for every block but the last, which the
+// caller hands over when it publishes the operand.
 template <int NCC, int KIND, bool STORE, bool MASK, int SRC = 0, int HSRC = SRC, bool DEEP = false, class Hook = NoBlockHook>
 __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* __restrict__ bias,
                                                    const uint32_t (&a8)[8], const float* __restrict__ w_sigma,
@@ -307,7 +308,6 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         tmem_regs_ready(rc); tmem_regs_ready(rd);
         fwd_epilogue32<6, KIND, STORE, MASK, SRC, HSRC>(rc, bias, a8, w_sigma, w_rgb2, acc, mscr);
         fwd_epilogue32<7, KIND, STORE, MASK, SRC, HSRC>(rd, bias, a8, w_sigma, w_rgb2, acc, mscr);
-        hook(3);
         return;
     }
 #if CNB_EPI_PREFETCH
@@ -325,7 +325,7 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         umma::tmem_ld_wait();
         fwd_epilogue32<CC, KIND, STORE, MASK, SRC, HSRC, P, P>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
         fwd_epilogue32<CC + 1, KIND, STORE, MASK, SRC, HSRC, P, P && (CC + 2 < NCC)>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
-        if constexpr (CC + 2 >= NCC) hook(CC >> 1);
+        // (the LAST block is handed over by the caller together with the operand's publication)
     };
     pair(std::integral_constant<int, 0>{});
     pair(std::integral_constant<int, 2>{});
@@ -333,38 +333,6 @@ __device__ __forceinline__ void fwd_epilogue_layer(uint32_t taddr, const float* 
         pair(std::integral_constant<int, 4>{});
         pair(std::integral_constant<int, 6>{});
     }
-}
-
-// A 256-column layer drained in the block order 1, 2, 3, 0 (non-DEEP form).  For the FIRST layer of a tile: block 0 of the
-// operand buffer still holds the positional encodings whose stash store was issued one short (K = 64) GEMM ago;
-// `before_block0()` (the wait for that store) is called only when the other three blocks are done.
-template <int KIND, bool MASK, int SRC, int HSRC, class Hook, class BeforeBlock0>
-__device__ __forceinline__ void fwd_epilogue_layer_rot(uint32_t taddr, const float* __restrict__ bias, const uint32_t (&a8)[8],
-                                                       const float* __restrict__ w_sigma, const float* __restrict__ w_rgb2,
-                                                       HeadAcc& acc, uint32_t* mscr, Hook hook, BeforeBlock0 before_block0) {
-    constexpr bool P = CNB_EPI_PREFETCH != 0;
-#if CNB_EPI_PREFETCH
-    float4 pre[2] = {ld_vec4<SRC>(bias + 64), ld_vec4<SRC>(bias + 68)};
-#else
-    float4* pre = nullptr;
-#endif
-    auto pair = [&](auto cc_tag, auto first_tag) {
-        constexpr int CC = decltype(cc_tag)::value;
-        constexpr bool FIRST = decltype(first_tag)::value;      // first pair of the rotated order (CC = 2)
-        uint32_t ra[32], rb[32];
-        umma::tmem_ld32(taddr + CC * 32, ra);
-        umma::tmem_ld32(taddr + CC * 32 + 32, rb);
-        if constexpr (!FIRST) hook(CC == 0 ? 3 : (CC >> 1) - 1);      // the block before this one in the rotated order
-        if constexpr (CC == 0) before_block0();
-        umma::tmem_ld_wait();
-        fwd_epilogue32<CC, KIND, true, MASK, SRC, HSRC, P && CC != 0, P>(ra, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
-        fwd_epilogue32<CC + 1, KIND, true, MASK, SRC, HSRC, P, P && CC != 0 && CC != 6>(rb, bias, a8, w_sigma, w_rgb2, acc, mscr, true, pre);
-        if constexpr (CC == 0) hook(0);
-    };
-    pair(std::integral_constant<int, 2>{}, std::true_type{});
-    pair(std::integral_constant<int, 4>{}, std::false_type{});
-    pair(std::integral_constant<int, 6>{}, std::false_type{});
-    pair(std::integral_constant<int, 0>{}, std::false_type{});
 }
 
 // NC (2 or 4) consecutive 32-column chunks of a layer: one thread's share when two warps split the columns of a row.
