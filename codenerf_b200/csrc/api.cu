@@ -46,6 +46,7 @@ Opt g_opts[] = {
     {"keep_weights", false, 0},   // 0: no L2 evict_last policy on the weight loads of the training kernel (default 1)
     {"stash_copy", false, 0},     // 1: the auxiliary warp copies the stash with ld.shared / st.global instead of TMA bulk stores (slower)
     {"stash_lanes", false, 0},    // bulk stores per stashed operand image (32 = 2 KB pieces; 1, 2, 4, 8, 16)
+    {"share_fills", false, 0},    // 0: CTA pairs: every GEMM streams its own copy of the layer's weights (default 1: group Y reuses group X's fill)
     {"stash_early", false, 0},    // 0: one stash hand-off per operand image (after the whole epilogue) instead of one per 64-column block
     {"early_pieces", false, 0},   // bulk stores per signalled block of the early stash (1, 2, 4, 8)
     {"experiment", false, 0},     // timing experiments (bit mask, WRONG results): 1 no stash stores, 2 group Y reuses group X's weight fills

@@ -95,6 +95,8 @@ struct BwdParams {
     float *d_wrgb2, *d_brgb2;
     int stash_lanes;                // lanes of the auxiliary warp that issue the bulk stores of an operand image (32: 2 KB pieces)
     int keep_weights;               // 1: weight loads carry an L2 evict_last policy while the stash streams through L2
+    int share_fills;                // CTA pairs: group Y's GEMM of a layer whose weights fill the ring exactly once (4 chunks) reuses the
+                                    // fill of group X's GEMM of the same layer, issued just before it -- half the weight stream
     int stash_early;                // 1: every 64-column block of an operand image is handed to the auxiliary warp's bulk store as soon as
                                     // the epilogue has written it (4 signals per image instead of 1): the store drains during the epilogue
     int early_pieces;               // (stash_early) bulk stores per signalled part, one lane each
@@ -411,7 +413,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                             if (2 * r + g >= UN) continue;
                             const FwdLayer& L = p.layers[op];
                             const int n_dir = L.has_dir ? L.n_halves : 0;
-                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph, pol_w, g == 1 && (p.experiment & 2));
+                            if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph, pol_w,
+                                                             g == 1 && ((p.experiment & 2) || (p.share_fills && L.n_kchunks + (L.has_dir ? 1 : 0) == kNumStages)));
                             else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                         }
                 if (i >= LA)
@@ -419,7 +422,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) k_mlp_bwd(const __grid_constan
                         for (int g = 0; g < 2; ++g) {
                             if (2 * r + g >= UN) continue;
                             const BwdStep& B = p.steps[s];
-                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph, pol_w, g == 1 && (p.experiment & 2));
+                            if (CG == 2) produce_stages_2cta(&p.maps, B.w_off, B.n_kchunks, 2, 0, rank, sW, w_full, w_empty, stage, ph, pol_w,
+                                                             g == 1 && ((p.experiment & 2) || (p.share_fills && B.n_kchunks == kNumStages)));
                             else produce_stages<MC>(p.packed + B.w_off, B.n_kchunks * 2, 0, sW, w_full, w_empty, stage, ph, rank, nullptr, pol_w);
                         }
             }
@@ -1564,6 +1568,7 @@ int run_mlp_bwd(const cnb_net_config* c, const float* const* P, const void* pack
     bp.stash = d_params ? 1 : 0; bp.stashA = stashA; bp.stashD = stashD; bp.dspre = dspre_buf;
     // column sums of dY: with a weight-gradient pass K3 reduces them from the stash for free; otherwise the aux
     // warps of K2 do it, and only for the folded layers (the latent-code gradients need nothing else)
+    bp.share_fills = cnb_option("share_fills", 1) != 0 ? 1 : 0;
     bp.colsum_layers = 0u;
     if (!d_params)
         for (int l = 0; l < nl; ++l) if (pl.fwd[l].folded >= 0) bp.colsum_layers |= 1u << l;
