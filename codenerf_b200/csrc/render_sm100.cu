@@ -47,6 +47,7 @@ struct FwdParams {
     int64_t n_rays, S;            // rays / rows of THIS launch
     int64_t ray_offset;           // mode 0: global index of this launch's first ray (sub-batching)
     int white_bg, ring_cap;
+    int share_fills;                // CTA pairs: group Y's GEMM reuses group X's weight fill of a layer that fills the ring exactly once
     int stage_bias;               // 1: shared memory has room for the bias / head-weight staging area
     float *rgb, *depth, *acc;
     float *spill_sig, *spill_rgb; // optional per-sample spill (launch-relative rows) for the training backward
@@ -196,7 +197,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_render_fwd(const __grid_constan
                     if (2 * r + g >= T) continue;
                     const FwdLayer& L = p.layers[l];
                     const int n_dir = L.has_dir ? L.n_halves : 0;
-                    if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph);
+                    if (CG == 2) produce_stages_2cta(&p.maps, L.w_off, L.n_kchunks, L.n_halves, L.has_dir, rank, sW, w_full, w_empty, stage, ph, 0ull,
+                                                     g == 1 && p.share_fills && L.n_kchunks + (L.has_dir ? 1 : 0) == kNumStages);
                     else produce_stages<MC>(p.packed + L.w_off, L.n_kchunks * L.n_halves + n_dir, n_dir, sW, w_full, w_empty, stage, ph, rank, &tr_we);
                 }
         tr_tot = (unsigned long long)(CNB_TR_NOW() - tr_t0);
@@ -1085,6 +1087,7 @@ int launch_fwd(const cnb_net_config* c, const float* const* P, const void* packe
     int grid = (int)(units < sms ? (units < 1 ? 1 : units) : sms);
     // CTA pairs by default (round 2, with the light-weight remote arrives of umma.cuh): +8-13 % in a same-session A/B
     const int use_pairs = (int)cnb_option("cta_pairs", 1);
+    fp.share_fills = cnb_option("share_fills", 1) != 0 ? 1 : 0;
     const char* form = getenv("CNB_FWD_KERNEL");       // "ts": the tensor-memory operand experiment (slower)
     const bool use_ts = cnb_option("fwd_kernel_ts", 0) != 0 || (form && form[0] == 't');
     if (!use_pairs && use_ts) {

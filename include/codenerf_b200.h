@@ -193,7 +193,7 @@ int cnb_debug_pipeline_timeouts(void);
  *   sub_tiles      128-row tiles per backward sub-batch (default 8192; the training stash needs ~1 MB of workspace
  *                  per tile, larger is faster; changes cnb_*_workspace_bytes)
  *   bwd_pairs, cta_pairs, weight_mcast, epi_warps, fwd_kernel_ts, k3_overlap, k3_sms, k3_items_per_sm_x10,
- *   head_mma, keep_weights, stash_early, early_pieces, stash_lanes, stash_copy
+ *   head_mma, keep_weights, share_fills, stash_early, early_pieces, stash_lanes, stash_copy, k3_grid
  *                  kernel variants kept for measurement
  *   stash_wrap, experiment
  *                  timing experiments that produce WRONG gradients on purpose (never set them outside a benchmark)

@@ -110,8 +110,10 @@ def test_backward_is_linear_in_the_seed():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("env", [{"CNB_BWD_PAIRS": "0"}, {"CNB_WEIGHT_MCAST": "2", "CNB_BWD_PAIRS": "0"}, {"CNB_K3_OVERLAP": "1"},
-                                 {"CNB_STASH_LANES": "32"}],
-                         ids=["single-cta", "multicast2", "k3-overlap", "stash-2KB-pieces"])
+                                 {"CNB_STASH_EARLY": "0", "CNB_STASH_LANES": "32"}, {"CNB_STASH_EARLY": "0"}, {"CNB_STASH_EARLY": "2"},
+                                 {"CNB_SHARE_FILLS": "0"}, {"CNB_HEAD_MMA": "0"}],
+                         ids=["single-cta", "multicast2", "k3-overlap", "late-stash-2KB-pieces", "late-stash", "stash-per-two-blocks",
+                              "own-weight-fills", "head-kernel"])
 def test_backward_kernel_variants_match_default(env):
     """The other forms of the training step (measured, not faster than the default CTA-pair kernel) give
     the default's gradients."""
