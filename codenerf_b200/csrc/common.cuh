@@ -101,6 +101,9 @@ inline void cnb_make_layout(const cnb_net_config* c, CnbLayout* L) {
     L->n_tensors = t;
 }
 
+#ifndef CNB_FAST_DDIV
+#define CNB_FAST_DDIV 1       // fp64 pixel / focal quotients from the host's reciprocal (0: __ddiv_rn)
+#endif
 // Camera / segment description passed by value to kernels that generate rays.
 struct CnbRaySource {
     const float* rays_o;      // explicit rays or nullptr
@@ -108,6 +111,7 @@ struct CnbRaySource {
     const float* c2w;         // [n_segments,16]
     const int32_t* pix_begin; // [n_segments] or nullptr
     double focal;
+    double inv_focal;         // RN(1 / focal), computed on the host (see cnb_ddiv_by)
     float focal32, half_w, half_h;
     int focal_is_f64, H, W;
     int rays_per_segment;
@@ -119,7 +123,7 @@ struct CnbRaySource {
 inline CnbRaySource cnb_make_ray_source(const cnb_ray_batch* r) {
     CnbRaySource s;
     s.rays_o = r->rays_o; s.viewdirs = r->viewdirs; s.c2w = r->c2w; s.pix_begin = r->pix_begin;
-    s.focal = r->focal; s.focal32 = (float)r->focal;
+    s.focal = r->focal; s.focal32 = (float)r->focal; s.inv_focal = 1.0 / r->focal;
     s.half_w = (float)(r->W * 0.5); s.half_h = (float)(r->H * 0.5);
     s.focal_is_f64 = r->focal_is_f64; s.H = r->H; s.W = r->W;
     s.rays_per_segment = r->rays_per_segment;
@@ -146,6 +150,15 @@ inline int cnb_validate_rays(const cnb_ray_batch* r) {
 // ---------------------------------------------------------------------------
 // Bit-exact ray generation -- reference src/utils.py:10-19.  Every rounding is
 // spelled out (_rn intrinsics never contract into FMAs); see SURVEY.md section 8a R1.
+// RN(a / b) from the correctly rounded reciprocal rb = RN(1 / b): q = RN(a rb) is within one ulp, the remainder
+// a - q b is exact in one FMA, and RN(q + rem rb) is then the correctly rounded quotient (Markstein's final division step).
+// Three fp64 instructions instead of the ~15 of a full division -- the per-sample ray generation inside the chain kernels was
+// bound by the fp64 pipe.  An exact q (rem == 0) is returned as is, which also keeps the sign of a zero quotient.
+__device__ __forceinline__ double cnb_ddiv_by(double a, double b, double rb) {
+    const double q = __dmul_rn(a, rb);
+    const double rem = __fma_rn(-q, b, a);
+    return rem == 0.0 ? q : __fma_rn(rem, rb, q);
+}
 __device__ __forceinline__ void cnb_pixel_ray(const CnbRaySource& s, const float* __restrict__ c2w, int pix,
                                               float o[3], float v[3]) {
     const int r = pix / s.W, c = pix - r * s.W;
@@ -153,8 +166,13 @@ __device__ __forceinline__ void cnb_pixel_ray(const CnbRaySource& s, const float
     const float fj = __fsub_rn((float)r, s.half_h);
     float dx, dy;
     if (s.focal_is_f64) {                              // fp64 focal tensor: divide in fp64, round once (utils.py:14-15)
+#if CNB_FAST_DDIV
+        dx = __double2float_rn(cnb_ddiv_by((double)fi, s.focal, s.inv_focal));
+        dy = __double2float_rn(cnb_ddiv_by(-(double)fj, s.focal, s.inv_focal));
+#else
         dx = __double2float_rn(__ddiv_rn((double)fi, s.focal));
         dy = __double2float_rn(__ddiv_rn(-(double)fj, s.focal));
+#endif
     } else {
         dx = __fdiv_rn(fi, s.focal32);
         dy = __fdiv_rn(-fj, s.focal32);

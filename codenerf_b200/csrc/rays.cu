@@ -22,7 +22,7 @@ extern "C" int cnb_get_rays(int H, int W, double focal, int focal_is_f64, const 
     if (H <= 0 || W <= 0 || !(focal > 0.0) || !c2w || !rays_o || !viewdirs) return CNB_E_INVALID;
     if ((int64_t)H * W > (int64_t)1 << 30) return CNB_E_UNSUPPORTED;
     CnbRaySource s = {};
-    s.c2w = c2w; s.focal = focal; s.focal32 = (float)focal; s.focal_is_f64 = focal_is_f64;
+    s.c2w = c2w; s.focal = focal; s.inv_focal = 1.0 / focal; s.focal32 = (float)focal; s.focal_is_f64 = focal_is_f64;
     s.H = H; s.W = W; s.half_w = (float)(W * 0.5); s.half_h = (float)(H * 0.5);
     const int n = H * W;
     k_get_rays<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(s, n, rays_o, viewdirs);
