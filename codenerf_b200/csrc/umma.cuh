@@ -2,6 +2,7 @@
 // 1-D form), tcgen05 tensor-core MMA with TMEM accumulators, descriptors.
 // Inline PTX only; compile with -gencode arch=compute_100a,code=sm_100a.
 #pragma once
+#include <cstdio>
 #include <cuda_bf16.h>
 #include <stdint.h>
 
@@ -71,7 +72,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+#ifdef CNB_WATCHDOG_PRINT      // debugging aid: report the wait that timed out and carry on (results are garbage)
+        if (clock64() - t0 > 400000000LL) {
+            if ((threadIdx.x & 31) == 0) printf("TIMEOUT blk %d warp %d bar+%d parity %u\n", (int)blockIdx.x, (int)(threadIdx.x >> 5), (int)(smem_u32(bar) & 0xfff), parity);
+            return;
+        }
+#else
         if (clock64() - t0 > kWatchdogCycles) mbar_watchdog_trip(1u);
+#endif
     }
 }
 
